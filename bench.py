@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- encrypted images/s of the keyed-layer forward path on B200.
+
+Workload (BASELINE.json configs[1]): CIFAR-10 AllConvNet 3x32x32, hierarchical block-permutation keys
+(`np.random.seed(0); Keynet((3,32,32), net, global_geometric='hierarchical_permutation',
+hierarchical_blockshape=(2,2), hierarchical_permute_at_level=(0,1))`), batch 4096 per GPU, synthetic
+images, numpy-seeded random-init weights.  One step = sensor.encrypt() + knet.forward() over one batch:
+1 layout kernel + 12 SpMM launches (+ReLU fused) + 1 layout kernel.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--net acn|lenet]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1: data-parallel replicas)
+  python bench.py --impl reference ...      (CPU arm: the oracle port of the reference's scipy path, all host threads)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
+through the host-buffer API (pinned H2D of the images and D2H of the logits inside the timed region);
+`roofline` = the dominant SpMM launch against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+`cpu_baseline` = the oracle port timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def numpy_weights(net, seed):
+    """Deterministic kaiming-uniform-like init from numpy's legacy RNG (same as tests/golden/make_golden.py)."""
+    import torch
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for (name, p) in net.named_parameters():
+            fan_in = int(np.prod(p.shape[1:])) if p.ndim > 1 else int(p.shape[0])
+            bound = 1.0 / np.sqrt(max(1, fan_in))
+            p.copy_(torch.from_numpy(rs.uniform(-bound, bound, size=tuple(p.shape)).astype(np.float32)))
+    return net
+
+
+def workload(name):
+    from keynet_b200 import nets
+    if name == 'acn':
+        return dict(net=numpy_weights(nets.AllConvNet(batchnorm=False), 0).eval(), inshape=(3, 32, 32),
+                    keys=dict(global_geometric='hierarchical_permutation', hierarchical_blockshape=(2, 2), hierarchical_permute_at_level=(0, 1)),
+                    label='AllConvNet 3x32x32, hierarchical block-permutation keys (BASELINE configs[1])')
+    if name == 'lenet':
+        return dict(net=numpy_weights(nets.LeNet_AvgPool(), 0).eval(), inshape=(1, 28, 28), keys=dict(global_geometric='permutation'),
+                    label='LeNet_AvgPool 1x28x28, PermutationKeynet (BASELINE configs[0])')
+    raise ValueError(name)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return (float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)')
+        except Exception:
+            pass
+    return (HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        (sm, smax, reasons) = ([], [], set())
+        for r in self.rows:
+            f = [t.strip() for t in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for (name, v) in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# =================================================================================================
+def oracle_layers_from_gpu(sensor, knet):
+    """Copy the (bit-exact, verified) compiled matrices to the host for the CPU baseline."""
+    from oracle import keynet_oracle as ko
+    layers = []
+    (ip, ix, dt) = sensor.W.csr_arrays()
+    layers.append((ko.csr(sensor.W.shape, ip, ix, dt), False))
+    for (k, L) in knet.keyedlayers():
+        (ip, ix, dt) = L.W.csr_arrays()
+        layers.append((ko.csr(L.W.shape, ip - ip[0], ix, dt), bool(L._fused_relu)))
+    return layers
+
+
+def oracle_layers_on_cpu(wl):
+    """Reference arm: key the network on the CPU with the oracle (Toeplitz + two SpGEMMs per layer), no GPU."""
+    from oracle import keynet_oracle as ko
+    from keynet_b200 import system, torch as ktorch
+    from torch import nn
+    recorded = []
+
+    def f_layergen(module, inshape, outshape, A, Ainv):
+        k = lambda K: None if K is None else ko.monomial_key(K.perm, K.scale)
+        if isinstance(module, nn.Conv2d):
+            W = ko.toeplitz_conv2d(inshape, module.weight.detach().numpy(), module.bias.detach().numpy(), module.stride[0])
+        elif isinstance(module, nn.AvgPool2d):
+            ks = module.kernel_size if isinstance(module.kernel_size, int) else module.kernel_size[0]
+            st = module.stride if isinstance(module.stride, int) else module.stride[0]
+            W = ko.toeplitz_avgpool2d(inshape, ks, st)
+        elif isinstance(module, nn.Linear):
+            W = ko.linear_matrix(module.weight.detach().numpy(), module.bias.detach().numpy())
+        else:
+            raise ValueError(str(type(module)))
+        What = ko.key_compile(k(A), W, k(Ainv))
+
+        class Rec(nn.Module):       # stands in for a KeyedLayer inside KeyedModel's Sequential
+            def fuse_relu(self, flag=True):
+                self.relu = bool(flag)
+                return self
+        r = Rec(); r.W = What; r.relu = False
+        recorded.append(r)
+        return r
+    np.random.seed(0)
+    f_keypair = system.keypair_policy(**wl['keys'])
+    (A, Ainv) = f_keypair('input', wl['inshape'])
+    system.KeyedModel(wl['net'], wl['inshape'], Ainv, f_keypair, f_layergen)
+    return [(ko.monomial_key(A.perm, A.scale), False)] + [(r.W, r.relu) for r in recorded]
+
+
+def time_oracle(layers, inshape, n_images, threads, repeats=1):
+    from oracle import keynet_oracle as ko
+    rs = np.random.RandomState(0)
+    x = ko.affine_to_linear(rs.randn(n_images, *inshape).astype(np.float32))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        y = ko.keyed_forward(layers, x, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    ko.linear_to_affine(y)
+    return best
+
+
+def cpu_baseline(layers, inshape, budget_s=12.0):
+    from oracle import keynet_oracle as ko
+    threads = ko.max_threads()
+    t_probe = time_oracle(layers, inshape, 2, threads)
+    n = int(max(2, min(256, (budget_s / max(t_probe / 2.0, 1e-6)))))
+    dt = time_oracle(layers, inshape, n, threads)
+    return {'value': n / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+            'sample': '%d images through the same compiled layer stack, oracle csr_matvecs port (OpenMP over rows), %.1f s' % (n, dt)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: rank 0 only; the oracle port keys and runs the same workload on the host cores."""
+    if rank != 0:
+        return
+    from oracle import keynet_oracle as ko
+    wl = workload(args.net)
+    layers = oracle_layers_on_cpu(wl)
+    threads = ko.max_threads()
+    t_probe = time_oracle(layers, wl['inshape'], 2, threads)
+    n = int(max(1, min(64, 4.0 / max(t_probe / 2.0, 1e-6))))       # ~4 s of CPU work per step
+    for _ in range(max(1, min(args.warmup, 1))):
+        time_oracle(layers, wl['inshape'], n, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_oracle(layers, wl['inshape'], n, threads)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    out = {'impl': 'reference', 'metric': 'encrypted_images_per_sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': wl['label'], 'images_per_step': n, 'note': 'CPU arm: oracle port of the reference scipy path; each step is a bounded sample of the workload'},
+           'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': '%d images per step, %d steps' % (n, args.steps)},
+           'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+# =================================================================================================
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=4096, help='images per GPU per step')
+    ap.add_argument('--net', default='acn', choices=['acn', 'lenet'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from keynet_b200 import system, engine, _native
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _native.lib()
+
+    wl = workload(args.net)
+    N = args.batch
+    t0 = time.perf_counter()
+    np.random.seed(0)
+    (sensor, knet) = system.Keynet(wl['inshape'], wl['net'], **wl['keys'])
+    torch.cuda.synchronize()
+    t_compile = time.perf_counter() - t0
+
+    K = args.steps
+    plan = engine.ForwardPlan(sensor, knet, N, use_graph=False, time_layers=True, event_sets=K)
+    g = torch.Generator(device='cuda').manual_seed(rank)
+    images = torch.randn((N,) + wl['inshape'], device='cuda', generator=g)      # synthetic, resident in HBM
+    plan.images.copy_(images.reshape(N, -1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for _ in range(args.warmup):
+        plan.run_device()
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    (e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e0.record()
+    for k in range(K):
+        plan.event_set = k
+        plan.run_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = plan.launches_per_run * K
+
+    # ---- end to end with host buffers -------------------------------------------------------
+    host_in = torch.randn((N,) + wl['inshape']).pin_memory()
+    host_out = torch.empty((N, plan.K), dtype=torch.float32).pin_memory()
+    plan.time_layers = False
+    for _ in range(2):
+        plan.run_host(host_in, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        plan.run_host(host_in, host_out)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        (ms, ms_e2e) = (float(t[0]), float(t[1]))
+
+    if rank == 0:
+        (peak, peak_src) = hbm_peak()
+        # per-layer launch durations measured inside the timed region (CUDA events on the launch stream)
+        per_layer = plan.layer_times_ms_mean(K)
+        alg = dict(plan.algorithmic_bytes())
+        (dom, dom_ms) = max(per_layer, key=lambda kv: kv[1])
+        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+        total_alg = sum(alg.values())
+        roofline = {'bound': 'hbm', 'kernel': 'spmm_rowwarp_kernel<4> on layer %s' % dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'peak_source': peak_src, 'launch_ms': dom_ms, 'algorithmic_bytes_per_launch': alg[dom],
+                    'share_of_step': dom_ms / (ms / K),
+                    'network': {'algorithmic_bytes_per_step': total_alg, 'achieved': total_alg / (ms / K * 1e-3) / 1e9, 'frac': total_alg / (ms / K * 1e-3) / 1e9 / peak},
+                    'layers_ms': {k: round(v, 4) for (k, v) in per_layer}}
+        out = {'metric': 'encrypted_images_per_sec', 'value': world * N * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': args.warmup,
+               'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': wl['label'], 'batch_per_gpu': N, 'global_batch': N * world, 'parallelism': 'dp%d replicas, no collective' % world,
+                          'l2': 'inputs larger than L2: %.2f GB of CSR + %.2f GB of activations per step' % (sum(L[1].nnz() for L in plan.layers) * 8 / 1e9, sum((L[1].shape[0] + L[1].shape[1]) * N * 4 for L in plan.layers) / 1e9),
+                          'nnz': int(sum(L[1].nnz() for L in plan.layers)), 'key_compile_s': round(t_compile, 3)},
+               'e2e': {'value': world * N * K / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(host_in.numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4 + 4),
+                       'ms_per_step': ms_e2e / K},
+               'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(oracle_layers_from_gpu(sensor, knet), wl['inshape'])
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

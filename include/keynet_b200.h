@@ -1,0 +1,131 @@
+/*
+ * keynet_b200.h -- C ABI of libkeynet_b200.so: the B200 (sm_100a) implementation of the
+ * keyed-layer forward path of visym/keynet.
+ *
+ * The reference has no FFI: its operator boundary is the Python `SparseMatrix` protocol
+ * (keynet/sparse.py:419-514) plus the key-compile call site `A.dot(W).dot(Ainv)`
+ * (keynet/layer.py:35,46,59,70) and the Toeplitz builders (keynet/sparse.py:122-212).  Each
+ * entry point below names the reference interface it replaces.  The ctypes binding a
+ * maintainer would add to the reference is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory unless the name ends in `_host`;
+ *   - CSR: `indptr` int64 [n_rows+1] (absolute offsets into indices/data, so a row shard is
+ *     just `indptr + row_begin`), `indices` int32, `data` float32;
+ *   - dense operands are row-major: X is [n_cols][ldx], Y is [n_rows][ldy], n_vecs <= ld;
+ *     this is the reference's `W.torchdot(x.t())` operand (features x batch);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call
+ *     is asynchronous on that stream and re-entrant;
+ *   - return value: 0 on success, negative kn_status on failure; never throws.  The message
+ *     for the calling thread's last failure is kn_last_error().
+ *   - two-phase builders: `*_count` writes per-row entry counts, the caller scans them with
+ *     kn_exclusive_scan_i64, allocates indices/data, then calls `*_fill`.
+ */
+#ifndef KEYNET_B200_H
+#define KEYNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KN_ABI_VERSION 1
+
+typedef enum {
+    KN_OK = 0,
+    KN_ERR_INVALID_ARGUMENT = -1,
+    KN_ERR_CUDA = -2,
+    KN_ERR_UNSUPPORTED = -3
+} kn_status;
+
+/* flags for kn_spmm_csr_f32 */
+#define KN_SPMM_RELU 1u        /* fuse max(y,0): the unkeyed nn.ReLU appended at keynet/system.py:92 */
+
+int kn_abi_version(void);
+const char *kn_last_error(void);
+
+/* Device facts used to size grids (returns KN_ERR_CUDA if no device). */
+int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *total_mem_bytes);
+
+/* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------
+ * Replaces SparseMatrix.torchdot (keynet/sparse.py:488-492 -> scipy csr_matvecs), called from
+ * KeyedLayer.forward / .decrypt (keynet/layer.py:92,99) and KeyedSensor.encrypt (system.py:254).
+ * fp32 accumulate; each output element sums its row's entries in stored order. */
+int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *data,
+                    int64_t n_rows, int64_t n_cols,
+                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
+                    uint32_t flags, void *stream);
+
+/* ---- prefix sum: out[0]=0, out[i+1]=out[i]+in[i]; out has n+1 entries (in may alias out+1) */
+int kn_exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, void *stream);
+
+/* ---- Toeplitz construction ---------------------------------------------------------------
+ * Replaces sparse_toeplitz_conv2d / sparse_toeplitz_avgpool2d (keynet/sparse.py:122-212): the
+ * homogeneous CSR matrix of a 'same'-padded cross-correlation,
+ *   row (m,ku,kv) = m*Uo*Vo + ku*Vo + kv,  col (c,y,x) = c*U*V + y*V + x,  bias in column C*U*V,
+ *   last row = e_last.  Rows are emitted with ascending columns and explicit zeros kept.
+ * `weight`/`bias` must already carry the reference's offset rounding fl32(fl32(w+off)-off)
+ * (sparse.py:184-187,193-196) -- it is applied by the host wrapper.
+ * depthwise != 0: weight is [C][P][Q] and only channel c==m is emitted (avg-pool; the
+ * reference's C*C zero blocks are dropped by the key compile that always follows, layer.py:59).
+ * row_ids (nullable): emit only these source rows, in this order -- this is where the output
+ * permutation key and the row shard are applied; NULL = rows 0..n_rows-1. */
+typedef struct {
+    int32_t C, U, V;        /* input  channels, height, width */
+    int32_t M;              /* output channels */
+    int32_t P, Q;           /* kernel height, width (odd) */
+    int32_t stride;
+    int32_t depthwise;      /* 0: full conv, 1: channel-diagonal (avgpool) */
+    int32_t has_bias;       /* 1: homogeneous form with bias column and last row */
+} kn_conv2d_desc;
+
+int kn_toeplitz_conv2d_count(const kn_conv2d_desc *desc_host, const int64_t *row_ids, int64_t n_rows,
+                             int64_t *row_nnz, void *stream);
+int kn_toeplitz_conv2d_fill(const kn_conv2d_desc *desc_host, const float *weight, const float *bias,
+                            const int64_t *row_ids, int64_t n_rows,
+                            const int64_t *indptr, int32_t *indices, float *data, void *stream);
+
+/* Homogeneous matrix of nn.Linear, [[W, b],[0, 1]] with exact zeros dropped
+ * (keynet/torch.py:80-89 + keynet/layer.py:69).  weight is [n_out][n_in] row-major. */
+int kn_linear_count(const float *weight, const float *bias, int64_t n_out, int64_t n_in,
+                    const int64_t *row_ids, int64_t n_rows, int64_t *row_nnz, void *stream);
+int kn_linear_fill(const float *weight, const float *bias, int64_t n_out, int64_t n_in,
+                   const int64_t *row_ids, int64_t n_rows,
+                   const int64_t *indptr, int32_t *indices, float *data, void *stream);
+
+/* ---- key compile for monomial keys (permutation and/or diagonal gain) ----------------------
+ * Replaces `A.dot(W).dot(Ainv)` (keynet/layer.py:35,59,70 -> two scipy csr_matmat) when A and
+ * Ainv have one entry per row.  The row gather by A is done upstream (row_ids of the builders /
+ * kn_csr_gather_rows); this call applies, per stored entry (r, c, v):
+ *     c' = col_map[c]                         (Ainv[c, c'] is the entry of row c)
+ *     v' = fl32( fl32(row_scale[r]*v) * col_scale[c] )     (left product first, as the reference)
+ *     dropped if v' == 0                      (scipy SpGEMM drops exact zeros)
+ * and writes rows with ascending c' (canonical form).  col_map / row_scale / col_scale may be
+ * NULL (identity / 1.0).  No FMA contraction, no flush-to-zero: values are bit-exact with scipy. */
+int kn_keycompile_count(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
+                        const float *row_scale, const float *col_scale, int64_t *row_nnz, void *stream);
+int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows, int64_t n_cols,
+                       const int32_t *col_map, const float *row_scale, const float *col_scale,
+                       const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
+
+/* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left
+ * for explicit matrices, e.g. sensor keys / ReLU keys, keynet/layer.py:46). */
+int kn_csr_gather_rows_count(const int64_t *indptr, const int64_t *row_ids, int64_t n_rows, int64_t *row_nnz, void *stream);
+int kn_csr_gather_rows_fill(const int64_t *indptr, const int32_t *indices, const float *data,
+                            const int64_t *row_ids, int64_t n_rows,
+                            const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
+
+/* ---- activation layout helpers -------------------------------------------------------------
+ * affine_to_linear (keynet/torch.py:65-68) fused with the transpose the reference does at
+ * layer.py:92: images [n_vecs][dim] row-major -> X [dim+1][ldx] with a trailing row of ones. */
+int kn_affine_to_linear_t(const float *images, int64_t n_vecs, int64_t dim, float *X, int64_t ldx, void *stream);
+/* inverse: X [dim+1][ldx] -> out [n_vecs][dim]; *bad_count_dev (int32, device) receives the number of
+ * vectors whose homogeneous coordinate is not within atol of 1 (linear_to_affine raises on it, torch.py:74). */
+int kn_linear_to_affine_t(const float *X, int64_t ldx, int64_t n_vecs, int64_t dim, float *out,
+                          float atol, int32_t *bad_count_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEYNET_B200_H */

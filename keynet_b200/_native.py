@@ -1,0 +1,93 @@
+"""ctypes binding of libkeynet_b200.so (C ABI declared in include/keynet_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this module raises.
+Build the library with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libkeynet_b200.so')
+
+KN_SPMM_RELU = 1
+
+# every symbol include/keynet_b200.h declares (tests/test_abi.py checks the two lists agree)
+SYMBOLS = [
+    'kn_abi_version', 'kn_last_error', 'kn_device_info',
+    'kn_spmm_csr_f32', 'kn_exclusive_scan_i64',
+    'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
+    'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
+    'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
+]
+
+
+class kn_conv2d_desc(ctypes.Structure):
+    _fields_ = [('C', ctypes.c_int32), ('U', ctypes.c_int32), ('V', ctypes.c_int32), ('M', ctypes.c_int32),
+                ('P', ctypes.c_int32), ('Q', ctypes.c_int32), ('stride', ctypes.c_int32),
+                ('depthwise', ctypes.c_int32), ('has_bias', ctypes.c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises NativeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError('libkeynet_b200.so not found at %s -- build it with __graft_entry__.build(); '
+                          'keynet_b200 has no CPU fallback' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, u32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, ctypes.c_float
+    L.kn_abi_version.restype = i32
+    L.kn_abi_version.argtypes = []
+    L.kn_last_error.restype = ctypes.c_char_p
+    L.kn_last_error.argtypes = []
+    L.kn_device_info.restype = i32
+    L.kn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_int64)]
+    sig = {
+        'kn_spmm_csr_f32': [vp, vp, vp, i64, i64, vp, i64, vp, i64, i64, u32, vp],
+        'kn_exclusive_scan_i64': [vp, vp, i64, vp],
+        'kn_toeplitz_conv2d_count': [ctypes.POINTER(kn_conv2d_desc), vp, i64, vp, vp],
+        'kn_toeplitz_conv2d_fill': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, vp],
+        'kn_linear_count': [vp, vp, i64, i64, vp, i64, vp, vp],
+        'kn_linear_fill': [vp, vp, i64, i64, vp, i64, vp, vp, vp, vp],
+        'kn_keycompile_count': [vp, vp, vp, i64, vp, vp, vp, vp],
+        'kn_keycompile_fill': [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp],
+        'kn_csr_gather_rows_count': [vp, vp, i64, vp, vp],
+        'kn_csr_gather_rows_fill': [vp, vp, vp, vp, i64, vp, vp, vp, vp],
+        'kn_affine_to_linear_t': [vp, i64, i64, vp, i64, vp],
+        'kn_linear_to_affine_t': [vp, i64, i64, i64, vp, f32, vp, vp],
+    }
+    for (name, argtypes) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = i32
+        fn.argtypes = argtypes
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError('libkeynet_b200 call failed (%d): %s' % (rc, lib().kn_last_error().decode('utf-8', 'replace')))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError('keynet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')

@@ -1,0 +1,54 @@
+// common.cuh -- shared helpers for libkeynet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/keynet_b200.h"
+
+#define KN_API extern "C" __attribute__((visibility("default")))
+
+// thread-local last-error text, set by every failing entry point (abi.cu)
+void kn_set_error(const char *fmt, ...);
+
+#define KN_REQUIRE(cond, ...)                                   \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            kn_set_error(__VA_ARGS__);                          \
+            return KN_ERR_INVALID_ARGUMENT;                     \
+        }                                                       \
+    } while (0)
+
+#define KN_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            kn_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return KN_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define KN_CHECK_LAUNCH() KN_CUDA(cudaGetLastError())
+
+static inline int64_t kn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// number of SMs of the current device (cached); B200 = 148
+int kn_sm_count();
+
+// streaming (read-once) 128-bit load that does not allocate in L1
+__device__ __forceinline__ int4 kn_ldg_stream_int4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int kn_ldg_stream_i32(const int *p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float kn_ldg_stream_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}

@@ -1,0 +1,113 @@
+"""Batched forward engine: the keyed layer chain for a fixed batch size with pre-allocated, feature-major
+activation buffers, launched either eagerly or as one CUDA graph (the chain is launch-latency bound for
+LeNet-sized nets).  B200-side replacement for looping `KeyedLayer.forward` (keynet/system.py:130-133)."""
+import numpy as np
+import torch
+
+from . import _native
+from . import layer as _layer
+from .sparse import spmm
+
+
+class ForwardPlan(object):
+    """sensor.encrypt() + knet.forward() for batches of exactly N images.
+
+    run_device(images[N,C,H,W] cuda) -> logits[N,K] cuda     (everything stays in HBM)
+    run_host(images pinned host)     -> logits host tensor    (H2D + chain + D2H, checks the homogeneous coordinate)
+    """
+
+    def __init__(self, sensor, knet, batch, use_graph=True, time_layers=False, event_sets=1):
+        _native.require_cuda()
+        self.dev = torch.device('cuda', torch.cuda.current_device())
+        self.N = int(batch)
+        self.sensor = sensor
+        self.knet = knet
+        self.layers = [('sensor', sensor.W, False)] + [(k, L.W, L._fused_relu or 'ReLU' in L._layertype) for (k, L) in knet.keyedlayers()]
+        self.D = int(np.prod(sensor._inshape))
+        assert sensor.W.shape[1] == self.D + 1
+        self.K = self.layers[-1][1].shape[0] - 1
+        N = self.N
+        self.images = torch.empty((N, self.D), dtype=torch.float32, device=self.dev)
+        self.X0 = torch.empty((self.D + 1, N), dtype=torch.float32, device=self.dev)
+        self.acts = [torch.empty((W.shape[0], N), dtype=torch.float32, device=self.dev) for (_, W, _) in self.layers]
+        self.logits = torch.empty((N, self.K), dtype=torch.float32, device=self.dev)
+        self.bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.launches_per_run = 2 + len(self.layers)
+        self.time_layers = time_layers
+        # per-layer CUDA events on the launch stream, one set per timed step (read back after the timed region)
+        self.layer_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.layers]
+                             for _ in range(max(1, event_sets))] if time_layers else None
+        self.event_set = 0
+        self.graph = None
+        if use_graph and not time_layers:
+            self._capture()
+
+    # ---- the chain: 1 layout kernel + one SpMM per keyed layer + 1 layout kernel
+    def _chain(self):
+        L = _native.lib()
+        s = _native.stream_ptr()
+        _native.check(L.kn_affine_to_linear_t(_native.ptr(self.images), self.N, self.D, _native.ptr(self.X0), self.N, s))
+        x = self.X0
+        for (i, (name, W, relu)) in enumerate(self.layers):
+            if self.time_layers:
+                self.layer_events[self.event_set][i][0].record()
+            spmm(W, x, relu=relu, out=self.acts[i])
+            if self.time_layers:
+                self.layer_events[self.event_set][i][1].record()
+            x = self.acts[i]
+        _native.check(L.kn_linear_to_affine_t(_native.ptr(x), self.N, self.N, self.K, _native.ptr(self.logits), 1e-3, _native.ptr(self.bad), s))
+
+    def _capture(self):
+        self._chain()                      # warm-up outside capture (lazy module load, smem attributes)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._chain()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+
+    def _launch(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._chain()
+
+    def run_device(self, images=None):
+        """images: [N,C,H,W] (or [N,D]) float32 on this device, or None to reuse the staged batch."""
+        if images is not None:
+            self.images.copy_(images.reshape(self.N, self.D), non_blocking=True)
+        self._launch()
+        return self.logits
+
+    def run_host(self, images_host, out_host=None):
+        """End-to-end call with HOST buffers: H2D of the images, the whole chain, D2H of the logits."""
+        self.bad.zero_()
+        self.images.copy_(images_host.reshape(self.N, self.D), non_blocking=True)
+        self._launch()
+        out = out_host if out_host is not None else torch.empty((self.N, self.K), dtype=torch.float32, pin_memory=True)
+        out.copy_(self.logits, non_blocking=True)
+        bad = self.bad.cpu()               # synchronises the stream
+        if int(bad.item()) != 0:
+            raise ValueError('invalid affine vector: %d outputs lost the homogeneous coordinate' % int(bad.item()))
+        return out
+
+    def layer_times_ms_mean(self, n_sets):
+        """Mean launch duration of every layer's SpMM over the first n_sets recorded steps."""
+        assert self.layer_events is not None
+        torch.cuda.synchronize()
+        out = []
+        for (i, (name, _, _)) in enumerate(self.layers):
+            ts = [self.layer_events[k][i][0].elapsed_time(self.layer_events[k][i][1]) for k in range(n_sets)]
+            out.append((name, float(np.mean(ts))))
+        return out
+
+    def algorithmic_bytes(self):
+        """per layer nnz*8 + (R+1)*4 + (C+R)*N*4."""
+        out = []
+        for (name, W, _) in self.layers:
+            (R, C) = W.shape
+            out.append((name, W.nnz() * 8 + (R + 1) * 4 + (C + R) * self.N * 4))
+        return out

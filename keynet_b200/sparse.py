@@ -1,0 +1,556 @@
+"""Sparse algebra of the keyed-layer path on B200: device-resident CSR matrices, key matrices,
+Toeplitz construction and key compile.  Mirrors the public names of the reference's
+keynet/sparse.py; every heavy operation is a hand-written sm_100a kernel behind the C ABI
+(include/keynet_b200.h).  No scipy / torch.sparse / CPU fallback on the product path.
+
+Representation choices (B200-first, not a port):
+  * key matrices are never materialised as sparse matrices on the host: a permutation and/or
+    diagonal-gain key is a `MonomialKey` = (perm, scale) with A[r, perm[r]] = scale[r]; composing
+    keys is O(n) integer indexing + one fp32 multiply per row, done with the reference's fp32
+    rounding so results match its scipy SpGEMM chain bit-for-bit (system.py:467-468).
+  * layer matrices live on the GPU as CSR (int64 indptr, int32 indices, fp32 data) and are built
+    there: Toeplitz rows are written in closed form (csrc/toeplitz.cu), keys are folded in by
+    csrc/keycompile.cu.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import kn_conv2d_desc, ptr, stream_ptr, check
+from .util import blockview
+
+
+# =============================================================================================
+# Key matrices
+# =============================================================================================
+class MonomialKey(object):
+    """n x n matrix with exactly one stored entry per row: A[r, perm[r]] = scale[r].
+
+    Covers the reference's identity / permutation / hierarchical block permutation / memory-order
+    / diagonal gain keys and all their products (keynet/sparse.py:53-84,272-285,318-321)."""
+
+    def __init__(self, perm, scale=None):
+        self.perm = np.ascontiguousarray(perm, dtype=np.int64)
+        n = len(self.perm)
+        self.scale = np.ones(n, dtype=np.float32) if scale is None else np.ascontiguousarray(scale, dtype=np.float32)
+        assert self.scale.shape == (n,)
+        self.shape = (n, n)
+        self.dtype = np.float32
+        self.ndim = 2
+
+    def __repr__(self):
+        return '<keynet_b200.MonomialKey: n=%d, permuted=%s, scaled=%s>' % (self.shape[0], not self.is_unpermuted(), not self.is_unscaled())
+
+    # -- structure tests
+    def is_unpermuted(self):
+        return bool(np.array_equal(self.perm, np.arange(len(self.perm))))
+
+    def is_unscaled(self):
+        return bool(np.all(self.scale == np.float32(1.0)))
+
+    def is_identity(self):
+        return self.is_unpermuted() and self.is_unscaled()
+
+    @property
+    def nnz(self):
+        return len(self.perm)
+
+    # -- algebra (fp32 products rounded once, like scipy's csr_matmat on single-entry rows)
+    def dot(self, other):
+        """self . other.  other: MonomialKey -> MonomialKey; SparseMatrix -> SparseMatrix (row gather + scale)."""
+        if isinstance(other, MonomialKey):
+            assert self.shape[1] == other.shape[0], 'non-conformal keys %s, %s' % (str(self.shape), str(other.shape))
+            return MonomialKey(other.perm[self.perm], (self.scale * other.scale[self.perm]).astype(np.float32))
+        if isinstance(other, SparseMatrix):
+            return other._left_monomial(self)
+        raise TypeError('cannot multiply MonomialKey with %s' % str(type(other)))
+
+    def transpose(self):
+        n = len(self.perm)
+        (perm, scale) = (np.empty(n, dtype=np.int64), np.empty(n, dtype=np.float32))
+        perm[self.perm] = np.arange(n)
+        scale[self.perm] = self.scale
+        return MonomialKey(perm, scale)
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    def astype(self, dtype):
+        assert np.dtype(dtype) == np.float32
+        return self
+
+    def diagonal(self):
+        d = np.zeros(len(self.perm), dtype=np.float32)
+        on = self.perm == np.arange(len(self.perm))
+        d[on] = self.scale[on]
+        return d
+
+    # -- interop (tests, visualisation); not used by the product path
+    def todense(self):
+        D = np.zeros(self.shape, dtype=np.float32)
+        D[np.arange(len(self.perm)), self.perm] = self.scale
+        return D
+
+    def toscipy(self, format='csr'):
+        import scipy.sparse
+        n = len(self.perm)
+        return scipy.sparse.csr_matrix((self.scale, self.perm.astype(np.int32), np.arange(n + 1)), shape=self.shape).asformat(format)
+
+
+def is_key(A):
+    return isinstance(A, MonomialKey)
+
+
+def sparse_identity_matrix(n, dtype=np.float32):
+    return MonomialKey(np.arange(int(n)))
+
+
+def sparse_identity_matrix_like(A):
+    return MonomialKey(np.arange(A.shape[0]))
+
+
+def sparse_permutation_matrix(n, dtype=np.float32, withinverse=False):
+    """P[r, perm[r]] = 1 with perm drawn from numpy's global legacy RNG, consuming exactly the stream
+    the reference consumes (np.random.permutation over range(n), keynet/sparse.py:280-285)."""
+    P = MonomialKey(np.random.permutation(int(n)))
+    return (P, P.transpose()) if withinverse else P
+
+
+def sparse_uniform_random_diagonal_matrix(n, scale=1, bias=0, eps=1E-6, dtype=np.float32, withinverse=False):
+    """diag(scale*U[0,1) + eps + bias); the inverse is 1/d evaluated in float64 and then rounded to
+    float32, as the reference does (keynet/sparse.py:318-321)."""
+    d = np.array(scale * np.random.rand(int(n)) + eps + bias)      # float64
+    D = MonomialKey(np.arange(int(n)), d.astype(np.float32))
+    return (D, MonomialKey(np.arange(int(n)), (1.0 / d).astype(np.float32))) if withinverse else D
+
+
+def sparse_gaussian_random_diagonal_matrix(n, mu=1, sigma=1, eps=1E-6, withinverse=False, dtype=np.float32):
+    d = np.maximum(eps, np.array(sigma * np.random.randn(int(n)) + mu))
+    D = MonomialKey(np.arange(int(n)), d.astype(np.float32))
+    return (D, MonomialKey(np.arange(int(n)), (1.0 / d).astype(np.float32))) if withinverse else D
+
+
+def sparse_channelorder_to_pixelorder_matrix(shape, withinverse=False):
+    """Permutation taking a CxHxW (channel order) flattening to HxWxC (pixel order), keynet/sparse.py:53-62."""
+    img = np.arange(int(np.prod(shape))).reshape(shape)
+    P = MonomialKey(np.moveaxis(img, 0, 2).flatten())
+    return P if not withinverse else (P, P.transpose())
+
+
+def sparse_channelorder_to_blockorder_matrix(shape, blocksize, withinverse=True):
+    """Permutation taking CxHxW to Cx(H//B)x(W//B)xBxB block order, keynet/sparse.py:65-84."""
+    assert isinstance(shape, tuple) and len(shape) == 3, "Shape must be (C,H,W) tuple"
+    (C, H, W) = shape
+    if (H * W) % blocksize != 0:
+        warnings.warn('[keynet_b200.sparse.sparse_channelorder_to_blockorder]:  Ragged blockorder for blocksize=%d and shape=%s' % (blocksize, str(shape)))
+    (H_pad, W_pad) = (int(blocksize * np.ceil(H / float(blocksize))), int(blocksize * np.ceil(W / float(blocksize))))
+    order = blockview(np.arange(H_pad * W_pad).reshape(H_pad, W_pad), blocksize).flatten()[0:H * W]
+    if H_pad != H or W_pad != W:
+        raise ValueError('ragged block order (blocksize=%d, shape=%s) is not a permutation' % (blocksize, str(shape)))
+    perm = np.concatenate([order + c * H * W for c in range(C)])
+    A = MonomialKey(perm)
+    return A if not withinverse else (A, A.transpose())
+
+
+def sparse_affine_to_linear(A, bias=None, dtype=np.float32):
+    """[A 0; 0 1]: homogeneous augmentation of a key (keynet/sparse.py:87-96).  Keys with a bias
+    column are not monomial and belong to the general-key path."""
+    assert isinstance(A, MonomialKey), 'sparse_affine_to_linear expects a key matrix'
+    if bias is not None:
+        raise NotImplementedError('affine (bias) keys are not monomial: general key compile is a later scope row')
+    n = A.shape[0]
+    return MonomialKey(np.concatenate([A.perm, [n]]), np.concatenate([A.scale, np.ones(1, dtype=np.float32)]))
+
+
+def sparse_block_diagonal_repeat(B, shape):
+    """Key B repeated down the diagonal of an (N,N) matrix, truncated at N (the monomial case of the
+    reference's DiagonalTiledMatrix / sparse_block_diagonal, keynet/sparse.py:215-235,657-687)."""
+    assert isinstance(B, MonomialKey) and shape[0] == shape[1]
+    (n, h) = (int(shape[0]), B.shape[0])
+    reps = int(np.ceil(n / float(h)))
+    perm = (np.tile(B.perm, reps) + np.repeat(np.arange(reps) * h, h))[0:n]
+    scale = np.tile(B.scale, reps)[0:n]
+    if n % h != 0:
+        tail = np.arange(n - (n % h), n)          # ragged tail tile is the identity (sparse.py:680-681)
+        perm[tail] = tail
+        scale[tail] = 1.0
+    assert perm.max() < n
+    return MonomialKey(perm, scale)
+
+
+# =============================================================================================
+# Device CSR matrix
+# =============================================================================================
+def _device():
+    _native.require_cuda()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _scan_counts_inplace(indptr):
+    """indptr[1:] holds per-row counts on entry; on exit indptr is the exclusive prefix sum."""
+    n = indptr.numel() - 1
+    check(_native.lib().kn_exclusive_scan_i64(ptr(indptr[1:]) if n > 0 else None, ptr(indptr), n, stream_ptr()))
+
+
+def _two_phase(n_rows, count, fill, device):
+    """count(row_nnz) -> scan -> allocate -> fill(indptr, indices, data).  One host sync (the nnz readback)."""
+    indptr = torch.empty(n_rows + 1, dtype=torch.int64, device=device)
+    if n_rows > 0:
+        count(indptr[1:])
+    _scan_counts_inplace(indptr)
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(nnz, dtype=torch.int32, device=device)
+    data = torch.empty(nnz, dtype=torch.float32, device=device)
+    if n_rows > 0 and nnz > 0:
+        fill(indptr, indices, data)
+    return (indptr, indices, data)
+
+
+class SparseMatrix(object):
+    """Device-resident CSR matrix implementing the reference's SparseMatrix operator protocol
+    (keynet/sparse.py:419-514): torchdot / dot / matmul / nnz / transpose / tocoo / tocsr /
+    from_scipy_sparse / from_torch_dense / from_torch_conv2d."""
+
+    def __init__(self, A=None, device=None):
+        self.ndim = 2
+        self.dtype = np.float32
+        if A is None:
+            (self.shape, self._indptr, self._indices, self._data) = ((0, 0), None, None, None)
+            return
+        dev = device if device is not None else _device()
+        if isinstance(A, SparseMatrix):
+            (self.shape, self._indptr, self._indices, self._data) = (A.shape, A._indptr, A._indices, A._data)
+        elif isinstance(A, MonomialKey):
+            n = A.shape[0]
+            self.shape = A.shape
+            self._indptr = torch.arange(n + 1, dtype=torch.int64, device=dev)
+            self._indices = torch.from_numpy(A.perm.astype(np.int32)).to(dev)
+            self._data = torch.from_numpy(A.scale).to(dev)
+        elif isinstance(A, tuple) and len(A) == 4:
+            (shape, indptr, indices, data) = A
+            self.shape = (int(shape[0]), int(shape[1]))
+            self._indptr = torch.as_tensor(np.asarray(indptr) if not torch.is_tensor(indptr) else indptr).to(device=dev, dtype=torch.int64).contiguous()
+            self._indices = torch.as_tensor(np.asarray(indices) if not torch.is_tensor(indices) else indices).to(device=dev, dtype=torch.int32).contiguous()
+            self._data = torch.as_tensor(np.asarray(data) if not torch.is_tensor(data) else data).to(device=dev, dtype=torch.float32).contiguous()
+            assert self._indptr.numel() == self.shape[0] + 1 and self._indices.numel() == self._data.numel()
+        elif isinstance(A, np.ndarray):
+            M = self.from_torch_dense(torch.from_numpy(np.ascontiguousarray(A, dtype=np.float32)))
+            (self.shape, self._indptr, self._indices, self._data) = (M.shape, M._indptr, M._indices, M._data)
+        elif hasattr(A, 'tocsr'):     # scipy sparse (interop only)
+            M = self.from_scipy_sparse(A)
+            (self.shape, self._indptr, self._indices, self._data) = (M.shape, M._indptr, M._indices, M._data)
+        else:
+            raise AssertionError('Invalid input - %s' % str(type(A)))
+
+    def __repr__(self):
+        return '<keynet_b200.SparseMatrix: H=%d, W=%d, nnz=%d, backend=b200-csr>' % (self.shape[0], self.shape[1], self.nnz())
+
+    # ---- protocol --------------------------------------------------------------------------
+    def new(self):
+        return SparseMatrix()
+
+    def clone(self):
+        return SparseMatrix((self.shape, self._indptr.clone(), self._indices.clone(), self._data.clone()), device=self._data.device)
+
+    def nnz(self):
+        return int(self._data.numel()) if self._data is not None else 0
+
+    def from_torch_dense(self, A):
+        """Non-zero entries of a dense matrix, row-major (scipy coo_matrix(dense) semantics)."""
+        assert torch.is_tensor(A) and A.ndim == 2
+        dev = _device()
+        W = A.detach().to(device=dev, dtype=torch.float32).contiguous()
+        (R, C) = W.shape
+        # [[W],[.]] without the homogeneous row: reuse the linear builder with n_rows = R and no bias
+        L = _native.lib()
+        (indptr, indices, data) = _two_phase(
+            R,
+            lambda row_nnz: check(L.kn_linear_count(ptr(W), None, R, C, None, R, ptr(row_nnz), stream_ptr())),
+            lambda ip, ix, dt: check(L.kn_linear_fill(ptr(W), None, R, C, None, R, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+            dev)
+        return SparseMatrix(((R, C), indptr, indices, data), device=dev)
+
+    def from_scipy_sparse(self, A):
+        A = A.tocsr().astype(np.float32)
+        A.sum_duplicates()
+        A.sort_indices()
+        return SparseMatrix((A.shape, A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data), device=_device())
+
+    def from_torch_conv2d(self, inshape, w, b, stride):
+        return sparse_toeplitz_conv2d(inshape, w.detach(), bias=b.detach() if b is not None else None, stride=stride)
+
+    def torchdot(self, x_torch, relu=False):
+        """SpMM W . x for x of shape (C, N); returns (R, N) float32 on x's device.
+
+        Replaces keynet/sparse.py:488-492.  A transposed view of a feature-major activation (what
+        KeyedLayer.forward passes) is consumed without a copy; CPU tensors are staged through the GPU."""
+        assert x_torch.ndim == 2 and x_torch.shape[0] == self.shape[1], "Non-conformal shape for W=%s, x=%s" % (str(self.shape), str(tuple(x_torch.shape)))
+        dev = self._data.device
+        on_host = not x_torch.is_cuda
+        x = x_torch.detach()
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        x = x.to(dev, non_blocking=True) if on_host else x
+        if not x.is_contiguous():
+            x = x.contiguous()
+        y = spmm(self, x, relu=relu)
+        return y.cpu() if on_host else y
+
+    def dot(self, x_numpy):
+        if isinstance(x_numpy, MonomialKey):
+            return self.clone().matmul(x_numpy)
+        assert isinstance(x_numpy, np.ndarray)
+        x = torch.from_numpy(np.ascontiguousarray(x_numpy, dtype=np.float32))
+        return self.torchdot(x.reshape(self.shape[1], -1)).numpy()
+
+    def matmul(self, A):
+        """In-place self <- self . A for a monomial key A (column reindex + scale + zero drop + sort),
+        the right-hand SpGEMM of keynet/layer.py:35 / keynet/sparse.py:472-480."""
+        if not isinstance(A, MonomialKey):
+            raise NotImplementedError('matmul with a general sparse matrix is a later scope row (SURVEY.md 8f-2)')
+        assert self.shape[1] == A.shape[0]
+        (self._indptr, self._indices, self._data) = _keycompile((self._indptr, self._indices, self._data), self.shape[0], self.shape[1],
+                                                                None, A, self._data.device)
+        self.shape = (self.shape[0], A.shape[1])
+        return self
+
+    def _left_monomial(self, A):
+        """A . self for a monomial key A: row gather + row scale + zero drop."""
+        assert A.shape[1] == self.shape[0]
+        dev = self._data.device
+        L = _native.lib()
+        n = A.shape[0]
+        rows = torch.from_numpy(A.perm).to(dev)
+        (indptr, indices, data) = _two_phase(
+            n,
+            lambda row_nnz: check(L.kn_csr_gather_rows_count(ptr(self._indptr), ptr(rows), n, ptr(row_nnz), stream_ptr())),
+            lambda ip, ix, dt: check(L.kn_csr_gather_rows_fill(ptr(self._indptr), ptr(self._indices), ptr(self._data), ptr(rows), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+            dev)
+        (indptr, indices, data) = _keycompile((indptr, indices, data), n, self.shape[1], A, None, dev)
+        return SparseMatrix(((n, self.shape[1]), indptr, indices, data), device=dev)
+
+    def transpose(self):
+        """In-place transpose (plumbing, not on the forward path): stable sort of the COO form by column."""
+        (R, C) = self.shape
+        rows = torch.repeat_interleave(torch.arange(R, device=self._data.device, dtype=torch.int64), self._indptr[1:] - self._indptr[:-1])
+        key = self._indices.to(torch.int64) * R + rows
+        order = torch.argsort(key)
+        counts = torch.bincount(self._indices.to(torch.int64), minlength=C)
+        indptr = torch.zeros(C + 1, dtype=torch.int64, device=self._data.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        (self._indptr, self._indices, self._data) = (indptr, rows[order].to(torch.int32).contiguous(), self._data[order].contiguous())
+        self.shape = (C, R)
+        return self
+
+    def tocsr(self):
+        return self
+
+    def tocsc(self):
+        raise NotImplementedError('CSC storage is not used on the B200 path')
+
+    def csr_arrays(self):
+        """(indptr int64, indices int32, data float32) as numpy arrays on the host (canonical: sorted columns)."""
+        return (self._indptr.cpu().numpy(), self._indices.cpu().numpy(), self._data.cpu().numpy())
+
+    def tocoo(self):
+        import scipy.sparse
+        (ip, ix, dt) = self.csr_arrays()
+        return scipy.sparse.csr_matrix((dt, ix, ip), shape=self.shape).tocoo()
+
+    def todense(self):
+        (ip, ix, dt) = self.csr_arrays()
+        D = np.zeros(self.shape, dtype=np.float32)
+        D[np.repeat(np.arange(self.shape[0]), np.diff(ip)), ix] = dt
+        return D
+
+    def row_slice(self, r0, r1):
+        """Rows [r0, r1) as a view-like SparseMatrix sharing indices/data (indptr offsets stay absolute)."""
+        M = SparseMatrix()
+        (M.shape, M._indptr, M._indices, M._data) = ((r1 - r0, self.shape[1]), self._indptr[r0:r1 + 1], self._indices, self._data)
+        return M
+
+
+# =============================================================================================
+# SpMM
+# =============================================================================================
+def spmm(W, x, relu=False, out=None):
+    """y[R, N] = W . x[C, N] (+ReLU) on the current CUDA stream.  x: contiguous float32 CUDA tensor."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.ndim == 2 and x.is_contiguous()
+    assert x.shape[0] == W.shape[1], "Non-conformal shape for W=%s, x=%s" % (str(W.shape), str(tuple(x.shape)))
+    (R, N) = (W.shape[0], x.shape[1])
+    y = out if out is not None else torch.empty((R, N), dtype=torch.float32, device=x.device)
+    assert y.shape == (R, N) and y.is_contiguous()
+    check(_native.lib().kn_spmm_csr_f32(ptr(W._indptr), ptr(W._indices), ptr(W._data), R, W.shape[1],
+                                        ptr(x), N, ptr(y), N, N, _native.KN_SPMM_RELU if relu else 0, stream_ptr()))
+    return y
+
+
+# =============================================================================================
+# Toeplitz construction + key compile
+# =============================================================================================
+def _offset_round(values, emitted_min):
+    """fl32(fl32(w + off) - off) with off = fl32(|min|+1): the reference's sparsity-preserving offset
+    (keynet/sparse.py:184-187,193-196) leaves every stored value rounded this way."""
+    off = np.float32(np.abs(np.float32(emitted_min)) + np.float32(1.0))
+    v = (np.asarray(values, dtype=np.float32) + off).astype(np.float32)
+    return (v - off).astype(np.float32)
+
+
+def _emitted_taps(U, k, stride):
+    """Which of the k taps along one axis are ever in bounds for some strided output position."""
+    h = (k - 1) // 2
+    u = np.arange(0, U, stride)
+    return np.array([np.any((u + p >= 0) & (u + p < U)) for p in range(-h, h + 1)])
+
+
+def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None):
+    """Apply column map/scales of Ainv and row scales of A to an already row-gathered CSR."""
+    (indptr, indices, data) = csr
+    L = _native.lib()
+    row_scale = None
+    if A is not None and not A.is_unscaled():
+        rs = A.scale if row_scale_slice is None else A.scale[row_scale_slice]
+        row_scale = torch.from_numpy(np.ascontiguousarray(rs)).to(dev)
+    (col_map, col_scale) = (None, None)
+    if Ainv is not None:
+        assert Ainv.shape[0] == n_cols
+        if not Ainv.is_unpermuted():
+            col_map = torch.from_numpy(Ainv.perm.astype(np.int32)).to(dev)
+        if not Ainv.is_unscaled():
+            col_scale = torch.from_numpy(Ainv.scale).to(dev)
+    return _two_phase(
+        n_rows,
+        lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols, ptr(col_map), ptr(row_scale), ptr(col_scale),
+                                                      ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+        dev)
+
+
+def _row_ids(A, n_total_rows, rows, dev):
+    """Source row of every output row: A.perm restricted to the row shard `rows` = (r0, r1)."""
+    (r0, r1) = (0, n_total_rows) if rows is None else (int(rows[0]), int(rows[1]))
+    assert 0 <= r0 <= r1 <= n_total_rows
+    if A is None or A.is_unpermuted():
+        ids = None if (r0 == 0 and r1 == n_total_rows) else torch.arange(r0, r1, dtype=torch.int64, device=dev)
+    else:
+        ids = torch.from_numpy(np.ascontiguousarray(A.perm[r0:r1])).to(dev)
+    return (ids, r0, r1)
+
+
+def _toeplitz_rows(desc, weight, bias, ids, n_rows, dev):
+    L = _native.lib()
+    w = torch.from_numpy(np.ascontiguousarray(weight, dtype=np.float32)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).to(dev) if bias is not None else None
+    return _two_phase(
+        n_rows,
+        lambda row_nnz: check(L.kn_toeplitz_conv2d_count(desc, ptr(ids), n_rows, ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_toeplitz_conv2d_fill(desc, ptr(w), ptr(b), ptr(ids), n_rows, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+        dev)
+
+
+def _conv_weights_rounded(inshape, f, bias, stride):
+    (C, U, V) = [int(s) for s in inshape]
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    (M, C2, P, Q) = f.shape
+    assert len(inshape) == 3 and f.ndim == 4
+    assert C2 == C, 'filter in-channels %d != input channels %d' % (C2, C)
+    assert P == Q and P % 2 == 1, 'filter must be square and odd'
+    assert U % stride == 0 and V % stride == 0, 'image size must be divisible by the stride'
+    mask = np.outer(_emitted_taps(U, P, stride), _emitted_taps(V, Q, stride))
+    fq = _offset_round(f, np.min(f[:, :, mask]))
+    bq = None
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        assert bias.shape == (M,)
+        bq = _offset_round(bias, np.min(bias))
+    return (fq, bq, (C, U, V, M, P, Q))
+
+
+def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None):
+    """W_hat = A . toeplitz(conv2d) . Ainv built on the GPU for monomial keys (keynet/layer.py:32-35).
+
+    rows=(r0, r1) builds only that row range of W_hat (row shard); indptr then has r1-r0+1 entries."""
+    dev = _device()
+    (fq, bq, (C, U, V, M, P, Q)) = _conv_weights_rounded(inshape, f, bias, stride)
+    R = M * (U // stride) * (V // stride) + 1
+    K = C * U * V + 1
+    desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1)
+    (ids, r0, r1) = _row_ids(A, R, rows, dev)
+    csr = _toeplitz_rows(desc, fq, bq, ids, r1 - r0, dev)
+    csr = _keycompile(csr, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
+    return SparseMatrix(((r1 - r0, K), *csr), device=dev)
+
+
+def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None):
+    """W_hat = A . toeplitz(avgpool) . Ainv (keynet/layer.py:56-59).  The reference builds C*C channel
+    pairs and lets the SpGEMM drop the zero ones; here only the channel diagonal is generated."""
+    dev = _device()
+    (C, U, V) = [int(s) for s in inshape]
+    k = int(kernel_size)
+    assert k % 2 == 1 and U % stride == 0 and V % stride == 0
+    w = np.float32(1.0 / (k * k))
+    # emitted-value minimum of the reference's dense-channel filter: 0 if any off-diagonal channel pair exists
+    emitted_min = np.float32(0.0) if C > 1 else w
+    wq = _offset_round(np.full((C, k, k), w, dtype=np.float32), emitted_min)
+    R = C * (U // stride) * (V // stride) + 1
+    K = C * U * V + 1
+    desc = kn_conv2d_desc(C, U, V, C, k, k, int(stride), 1, 0)     # zero bias column is dropped by the compile
+    (ids, r0, r1) = _row_ids(A, R, rows, dev)
+    csr = _toeplitz_rows(desc, wq, None, ids, r1 - r0, dev)
+    csr = _keycompile(csr, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
+    return SparseMatrix(((r1 - r0, K), *csr), device=dev)
+
+
+def keyed_linear(weight, bias, A, Ainv, rows=None):
+    """W_hat = A . [[W, b],[0, 1]] . Ainv (keynet/layer.py:69-70)."""
+    dev = _device()
+    L = _native.lib()
+    W = torch.as_tensor(weight).detach().to(device=dev, dtype=torch.float32).contiguous()
+    (n_out, n_in) = W.shape
+    b = torch.as_tensor(bias).detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
+    (ids, r0, r1) = _row_ids(A, n_out + 1, rows, dev)
+    n = r1 - r0
+    csr = _two_phase(
+        n,
+        lambda row_nnz: check(L.kn_linear_count(ptr(W), ptr(b), n_out, n_in, ptr(ids), n, ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_linear_fill(ptr(W), ptr(b), n_out, n_in, ptr(ids), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+        dev)
+    csr = _keycompile(csr, n, n_in + 1, A, Ainv, dev, row_scale_slice=slice(r0, r1))
+    return SparseMatrix(((n, n_in + 1), *csr), device=dev)
+
+
+def sparse_toeplitz_conv2d(inshape, f, bias=None, as_correlation=True, stride=1, format='csr'):
+    """Un-keyed sparse Toeplitz matrix of conv2d (explicit zeros kept), canonical CSR on the GPU.
+    Same contract as the reference's keynet/sparse.py:163-203:  conv2d(img, f) == W . img.flatten()."""
+    assert as_correlation, 'only cross-correlation (torch conv2d) is supported'
+    assert format == 'csr'
+    dev = _device()
+    f = f.detach().cpu().numpy() if torch.is_tensor(f) else f
+    bias = bias.detach().cpu().numpy() if torch.is_tensor(bias) else bias
+    (fq, bq, (C, U, V, M, P, Q)) = _conv_weights_rounded(inshape, f, bias, stride)
+    R = M * (U // stride) * (V // stride)
+    desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1 if bias is not None else 0)
+    n_rows = R + 1 if bias is not None else R
+    csr = _toeplitz_rows(desc, fq, bq, None, n_rows, dev)
+    return SparseMatrix(((n_rows, C * U * V + (1 if bias is not None else 0)), *csr), device=dev)
+
+
+def sparse_toeplitz_avgpool2d(inshape, filtershape, stride):
+    """Un-keyed Toeplitz matrix of avgpool2d exactly as the reference stores it (dense channel pairs with
+    explicit zeros, zero bias column; keynet/sparse.py:206-212)."""
+    (outchannel, inchannel, filtersize, filtersize2) = filtershape
+    F = np.zeros(filtershape, dtype=np.float32)
+    for k in range(0, outchannel):
+        F[k, k, :, :] = 1.0 / (filtersize * filtersize)
+    return sparse_toeplitz_conv2d(inshape, F, bias=np.zeros(outchannel, dtype=np.float32), stride=stride)
+
+
+def is_scipy_sparse(A):
+    try:
+        import scipy.sparse
+        return scipy.sparse.issparse(A)
+    except ImportError:
+        return False

@@ -1,0 +1,105 @@
+"""Host-side key logic (CPU): keygen / block permutation / key algebra against reference goldens.
+The keys are integer permutations and fp32 gains; parity is bit-exact."""
+import json
+
+import numpy as np
+import pytest
+
+from keynet_b200 import system, sparse, blockpermute, util
+from tests import golden_util as gu
+
+
+def _names(z):
+    return gu.jstr(z, 'names')
+
+
+@pytest.mark.parametrize('name', ['perm', 'gain', 'perm_gain', 'hier', 'hier_small', 'hrot', 'blockorder_perm', 'local_perm', 'local_gain', 'fc_perm'])
+def test_keygen_matches_reference(name):
+    z = gu.load('keygen_kat.npz')
+    kw = gu.jstr(z, name + '.args')
+    shape = tuple(kw.pop('shape'))
+    for k in ('hierarchical_blockshape', 'hierarchical_permute_at_level'):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    np.random.seed(11)
+    (A, Ainv) = system.keygen(shape, **kw)
+    for (K, pre) in ((A, name + '.A'), (Ainv, name + '.Ainv')):
+        (perm, scale) = gu.monomial_from_coo(z, pre)
+        assert np.array_equal(K.perm, perm), pre
+        assert np.array_equal(K.scale.view(np.uint32), scale.view(np.uint32)), pre
+    # A . Ainv is the identity permutation with gains within one ulp of 1
+    I = A.dot(Ainv)
+    assert I.is_unpermuted() and np.allclose(I.scale, 1.0, atol=2e-7)
+
+
+@pytest.mark.parametrize('name', ['bias', 'affine'])
+def test_keygen_general_keys_are_refused_loudly(name):
+    z = gu.load('keygen_kat.npz')
+    kw = gu.jstr(z, name + '.args')
+    shape = tuple(kw.pop('shape'))
+    with pytest.raises(NotImplementedError):
+        system.keygen(shape, **kw)
+
+
+def test_keygen_rejects_unknown_options():
+    with pytest.raises(ValueError):
+        system.keygen((1, 8, 8), 'nope', 'identity', 'identity', 'identity')
+    with pytest.raises(ValueError):
+        system.keygen((1, 8, 8), 'identity', 'identity', 'identity', 'identity', memoryorder='nope')
+    with pytest.raises(AssertionError):     # global permutation is not tile compressible (system.py:360)
+        system.keygen((1, 8, 8), 'permutation', 'identity', 'identity', 'identity', tileshape=(4, 4))
+
+
+def test_hierarchical_block_permutation_matches_reference():
+    z = gu.load('blockpermute_kat.npz')
+    for name in _names(z):
+        kw = gu.jstr(z, name + '.args')
+        P = blockpermute.hierarchical_block_permutation_matrix(tuple(kw['imgshape']), tuple(kw['blockshape']), kw['permute_at_level'],
+                                                               min_blocksize=8, seed=42, twist=kw['twist'], strict=False)
+        assert np.array_equal(P.perm, z[name + '.cols']), name
+        assert np.array_equal(np.sort(P.perm), np.arange(len(P.perm))), name
+
+
+def test_block_permute_image_form_equals_matrix_form():
+    """reference test/test_blockpermute.py:62 -- matrix form == image form (seed 42)."""
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 255, size=(64, 64, 3)).astype(np.uint8)
+    out = blockpermute.hierarchical_block_permute(img, (2, 2), [0, 1], min_blocksize=8, seed=42)
+    P = blockpermute.hierarchical_block_permutation_matrix(img.shape, (2, 2), [0, 1], min_blocksize=8, seed=42)
+    assert np.array_equal(img.flatten()[P.perm].reshape(img.shape), out)
+    with pytest.raises(ValueError):
+        blockpermute.hierarchical_block_permute(np.zeros((16, 16, 1)), (2, 2), [0, 1, 2], min_blocksize=8, seed=0)
+
+
+def test_monomial_key_algebra():
+    rs = np.random.RandomState(3)
+    n = 50
+    A = sparse.MonomialKey(rs.permutation(n), rs.rand(n).astype(np.float32) + 0.5)
+    B = sparse.MonomialKey(rs.permutation(n), rs.rand(n).astype(np.float32) + 0.5)
+    assert np.allclose(A.dot(B).todense(), A.todense().dot(B.todense()), rtol=1e-6)
+    assert np.array_equal(A.transpose().todense(), A.todense().T)
+    assert sparse.sparse_identity_matrix(n).is_identity()
+    H = sparse.sparse_affine_to_linear(A)
+    assert H.shape == (n + 1, n + 1) and H.perm[-1] == n and H.scale[-1] == 1.0
+    # products are rounded once in fp32, like scipy's SpGEMM on single-entry rows
+    import scipy.sparse
+    ref = A.toscipy().dot(B.toscipy()).tocsr(); ref.sort_indices()
+    got = A.dot(B).toscipy(); got.sort_indices()
+    assert np.array_equal(ref.indices, got.indices) and np.array_equal(ref.data.view(np.uint32), got.data.view(np.uint32))
+
+
+def test_permutation_consumes_same_rng_stream_as_reference_form():
+    np.random.seed(5)
+    a = np.random.permutation(list(range(0, 37)))      # reference form (sparse.py:283)
+    np.random.seed(5)
+    b = sparse.sparse_permutation_matrix(37).perm
+    assert np.array_equal(a, b)
+
+
+def test_find_closest_positive_divisor_and_blockview():
+    assert util.find_closest_positive_divisor(28, 8) == 7
+    assert util.find_closest_positive_divisor(224, 56) == 56
+    assert util.find_closest_positive_divisor(14, 56) == 14
+    assert util.find_closest_positive_divisor(7, 2) == 7
+    A = np.arange(36).reshape(6, 6)
+    assert np.array_equal(util.blockview(A, 3)[1, 0], A[3:6, 0:3])
