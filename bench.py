@@ -180,7 +180,7 @@ def cpu_baseline(layers, inshape, budget_s=12.0):
     from oracle import keynet_oracle as ko
     threads = ko.max_threads()
     t_probe = time_oracle(layers, inshape, 2, threads)
-    n = int(max(2, min(256, (budget_s / max(t_probe / 2.0, 1e-6)))))
+    n = int(max(2, min(8192, (budget_s / max(t_probe / 2.0, 1e-6)))))
     dt = time_oracle(layers, inshape, n, threads)
     return {'value': n / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
             'sample': '%d images through the same compiled layer stack, oracle csr_matvecs port (OpenMP over rows), %.1f s' % (n, dt)}
@@ -302,7 +302,9 @@ def main():
         (dom, dom_ms) = max(per_layer, key=lambda kv: kv[1])
         achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
         total_alg = sum(alg.values())
-        roofline = {'bound': 'hbm', 'kernel': 'spmm_rowwarp_kernel<4> on layer %s' % dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        domW = [W for (name, W, _) in plan.layers if name == dom][0]
+        kname = ('pg_simt_kernel (pattern groups %s)' % str(domW._pg.summary()['classes'])) if (domW._pg is not None and N >= 32 and N % 4 == 0) else 'spmm_rowwarp_kernel'
+        roofline = {'bound': 'hbm', 'kernel': '%s on layer %s' % (kname, dom), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                     'traffic': None, 'peak_source': peak_src, 'launch_ms': dom_ms, 'algorithmic_bytes_per_launch': alg[dom],
                     'share_of_step': dom_ms / (ms / K),
                     'network': {'algorithmic_bytes_per_step': total_alg, 'achieved': total_alg / (ms / K * 1e-3) / 1e9, 'frac': total_alg / (ms / K * 1e-3) / 1e9 / peak},

@@ -57,6 +57,30 @@ int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *
                     const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
                     uint32_t flags, void *stream);
 
+/* Same product for a subset of rows: output row i is written to Y[out_rows[i]] (out_rows NULL = identity).
+ * Used for the rows of a layer matrix that are not covered by pattern groups (below). */
+int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const float *data,
+                         int64_t n_rows, int64_t n_cols, const int32_t *out_rows,
+                         const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
+                         uint32_t flags, void *stream);
+
+/* ---- pattern-grouped execution format (csrc/pgroup.cu) ------------------------------------------
+ * B200 form of the reference's unique-tile storage (TiledMatrix / Conv2dTiledMatrix,
+ * keynet/sparse.py:517-835): rows with an identical column set form a group whose values are a dense
+ * G x K block; the product becomes one small GEMM per group with a gathered B operand.
+ *   kn_csr_row_pattern_hash  64-bit hash of every row's column set (grouping key)
+ *   kn_pg_verify             mismatch[i]=1 iff rows[i] and leaders[i] differ in their column lists
+ *   kn_pg_pack               rows[n_groups][G] -> cols[n_groups][K_pad], vals[n_groups][G][K_pad] (zero padded)
+ *   kn_spmm_pg_f32           Y[rows[g][:], :] = vals[g] . X[cols[g][:], :]  (+ReLU); fp32 FMA, K_pad % 32 == 0,
+ *                            n_vecs/ldx/ldy multiples of 4 */
+int kn_csr_row_pattern_hash(const int64_t *indptr, const int32_t *indices, int64_t n_rows, uint64_t *hash, void *stream);
+int kn_pg_verify(const int64_t *indptr, const int32_t *indices, const int64_t *rows, const int64_t *leaders, int64_t n,
+                 int32_t *mismatch, void *stream);
+int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data, const int64_t *rows,
+               int64_t n_groups, int32_t G, int32_t K_pad, int32_t *cols, float *vals, void *stream);
+int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int32_t G, int32_t K_pad,
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+
 /* ---- prefix sum: out[0]=0, out[i+1]=out[i]+in[i]; out has n+1 entries (in may alias out+1) */
 int kn_exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, void *stream);
 

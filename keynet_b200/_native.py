@@ -14,7 +14,8 @@ KN_SPMM_RELU = 1
 # every symbol include/keynet_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
     'kn_abi_version', 'kn_last_error', 'kn_device_info',
-    'kn_spmm_csr_f32', 'kn_exclusive_scan_i64',
+    'kn_spmm_csr_f32', 'kn_spmm_csr_rows_f32', 'kn_exclusive_scan_i64',
+    'kn_csr_row_pattern_hash', 'kn_pg_verify', 'kn_pg_pack', 'kn_spmm_pg_f32',
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
     'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
@@ -52,6 +53,11 @@ def lib():
     L.kn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_int64)]
     sig = {
         'kn_spmm_csr_f32': [vp, vp, vp, i64, i64, vp, i64, vp, i64, i64, u32, vp],
+        'kn_spmm_csr_rows_f32': [vp, vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u32, vp],
+        'kn_csr_row_pattern_hash': [vp, vp, i64, vp, vp],
+        'kn_pg_verify': [vp, vp, vp, vp, i64, vp, vp],
+        'kn_pg_pack': [vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp],
+        'kn_spmm_pg_f32': [vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_exclusive_scan_i64': [vp, vp, i64, vp],
         'kn_toeplitz_conv2d_count': [ctypes.POINTER(kn_conv2d_desc), vp, i64, vp, vp],
         'kn_toeplitz_conv2d_fill': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, vp],

@@ -1,0 +1,273 @@
+// pgroup.cu -- pattern-grouped execution format for keyed layer matrices and its fp32 SIMT kernel.
+//
+// Rows of a keyed Toeplitz matrix that belong to the same output pixel (all M output channels)
+// touch exactly the same columns -- also after permutation / gain keys, which only relabel rows
+// and columns.  Grouping rows by identical column set turns the matrix into
+//
+//     group g:   rows[g][0..G)          output rows (scattered by the output key)
+//                cols[g][0..K_pad)      the shared column list (gather list into X)
+//                vals[g][0..G)[0..K_pad) dense value block, zero padded
+//
+// and the SpMM into one small GEMM per group with a GATHERED B operand:
+//     Y[rows[g], :] = vals[g] (G x K) . X[cols[g], :] (K x N)
+// This is the B200 form of the reference's unique-tile storage (TiledMatrix / Conv2dTiledMatrix,
+// keynet/sparse.py:517-835: "unique spatial tile x dense (Cout,Cin) channel block"), but it is
+// discovered from the compiled CSR itself (row-pattern hashing), so it also applies where the
+// reference's tiling does not (global permutation keys, keynet/system.py:360).
+// Column indices are read once per group instead of once per stored value (4 instead of 8 bytes per
+// nnz), every gathered X row is reused by G output rows from shared memory, and the value block
+// is reused across the whole batch tile: the kernel is bound by the fp32 FMA pipe, not by L1/L2
+// gathers like the row-per-warp CSR kernel.
+//
+// Kernel: CTA = 256 threads = 8 warps, tile = (8*RW rows) x (128 batch columns), K chunks of 32
+// staged through a 3-stage cp.async ring (A: value rows, B: gathered X rows).  Warp w owns rows
+// [w*RW, (w+1)*RW), lane l owns 4 consecutive batch columns: RW*4 accumulators, A operands are
+// warp-broadcast LDS.128, B operands conflict-free LDS.128, 16*RW FFMA per (RW+4) LDS.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int KT = 32;       // k chunk
+constexpr int TN = 128;      // batch columns per CTA
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {    // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// order-independent 64-bit hash of a row's column set (+ its length); one warp per row
+__global__ void __launch_bounds__(kThreads)
+row_pattern_hash_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t n_rows, uint64_t *__restrict__ hash) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + warp; r < n_rows; r += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t beg = indptr[r], end = indptr[r + 1];
+        uint64_t h = 0;
+        for (int64_t e = beg + lane; e < end; e += 32) h += mix64((uint64_t)(uint32_t)indices[e]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+        if (lane == 0) hash[r] = mix64(h ^ ((uint64_t)(end - beg) << 40));
+    }
+}
+
+// mismatch[i] = 1 iff row rows[i] and row leaders[i] do not have identical column lists
+__global__ void __launch_bounds__(kThreads)
+pg_verify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                 const int64_t *__restrict__ rows, const int64_t *__restrict__ leaders, int64_t n, int32_t *__restrict__ mismatch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * (kThreads / 32) + warp; i < n; i += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t r = rows[i], l = leaders[i];
+        const int64_t rb = indptr[r], lb = indptr[l], len = indptr[r + 1] - rb;
+        int bad = (len != indptr[l + 1] - lb) ? 1 : 0;
+        if (!bad && r != l)
+            for (int64_t e = lane; e < len; e += 32) bad |= (indices[rb + e] != indices[lb + e]) ? 1 : 0;
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) mismatch[i] = bad;
+    }
+}
+
+// pack one class: cols[g][K_pad], vals[g][G][K_pad]; padding columns repeat the group's first column with value 0
+__global__ void __launch_bounds__(kThreads)
+pg_pack_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+               const int64_t *__restrict__ rows, int64_t n_groups, int G, int K_pad,
+               int32_t *__restrict__ cols, float *__restrict__ vals) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_rows = n_groups * G;
+    for (int64_t i = (int64_t)blockIdx.x * (kThreads / 32) + warp; i < n_rows; i += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t g = i / G;
+        const int64_t r = rows[i];
+        const int64_t beg = indptr[r];
+        const int len = (int)(indptr[r + 1] - beg);
+        float *__restrict__ v = vals + i * (int64_t)K_pad;
+        for (int k = lane; k < K_pad; k += 32) v[k] = (k < len) ? data[beg + k] : 0.0f;
+        if (i == g * G) {                                  // the group's first row writes the column list
+            int32_t *__restrict__ c = cols + g * (int64_t)K_pad;
+            const int32_t c0 = len > 0 ? indices[beg] : 0;
+            for (int k = lane; k < K_pad; k += 32) c[k] = (k < len) ? indices[beg + k] : c0;
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;                     // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+template <int RW, bool RELU>
+__global__ void __launch_bounds__(kThreads, 2)
+pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
+               int64_t n_groups, int G, int K_pad, int tiles_per_group,
+               const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
+{
+    constexpr int TM = 8 * RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*sA)[TM][KT] = reinterpret_cast<float (*)[TM][KT]>(smem_raw);
+    float (*sB)[KT][TN] = reinterpret_cast<float (*)[KT][TN]>(smem_raw + sizeof(float) * kStages * TM * KT);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t g = blockIdx.x / tiles_per_group;
+    const int rowtile = (int)(blockIdx.x - g * tiles_per_group);
+    const int64_t nbase = (int64_t)blockIdx.y * TN;
+    const int n_chunks = K_pad / KT;
+
+    const float *__restrict__ vbase = vals + (g * G + (int64_t)rowtile * TM) * K_pad;
+    const int32_t *__restrict__ cbase = cols + g * (int64_t)K_pad;
+    const int rows_here = min(TM, G - rowtile * TM);
+
+    auto load_stage = [&](int s, int kc) {
+        // A: TM rows x 8 chunks of 16 B
+#pragma unroll
+        for (int i = 0; i < (TM * 8 + kThreads - 1) / kThreads; i++) {
+            const int idx = tid + i * kThreads;
+            if (idx < TM * 8) {
+                const int r = idx >> 3, ch = idx & 7;
+                const bool ok = r < rows_here;
+                cp_async16(&sA[s][r][ch * 4], vbase + (ok ? ((int64_t)r * K_pad + kc * KT + ch * 4) : 0), ok);
+            }
+        }
+        // B: 32 gathered X rows x 32 chunks of 16 B (one warp per row: 512 contiguous bytes)
+#pragma unroll
+        for (int i = 0; i < (KT * (TN / 4)) / kThreads; i++) {
+            const int idx = tid + i * kThreads;
+            const int kr = idx >> 5, ch = idx & 31;
+            const int32_t c = __ldg(cbase + kc * KT + kr);
+            const int64_t n = nbase + ch * 4;
+            const bool ok = n < n_vecs;
+            cp_async16(&sB[s][kr][ch * 4], X + (int64_t)c * ldx + (ok ? n : 0), ok);
+        }
+    };
+
+    float acc[RW][4];
+#pragma unroll
+    for (int i = 0; i < RW; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++) {
+        if (s < n_chunks) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < n_chunks; kc++) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {   // prefetch chunk kc + kStages - 1 into the stage that was consumed in iteration kc - 1
+            const int nk = kc + kStages - 1;
+            if (nk < n_chunks) load_stage(nk % kStages, nk);
+            cp_async_commit();
+        }
+        const int s = kc % kStages;
+#pragma unroll
+        for (int k4 = 0; k4 < KT; k4 += 4) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(&sB[s][k4 + 0][lane * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&sB[s][k4 + 1][lane * 4]);
+            const float4 b2 = *reinterpret_cast<const float4 *>(&sB[s][k4 + 2][lane * 4]);
+            const float4 b3 = *reinterpret_cast<const float4 *>(&sB[s][k4 + 3][lane * 4]);
+#pragma unroll
+            for (int i = 0; i < RW; i++) {
+                const float4 a = *reinterpret_cast<const float4 *>(&sA[s][warp * RW + i][k4]);   // warp-broadcast
+                acc[i][0] = fmaf(a.x, b0.x, acc[i][0]); acc[i][1] = fmaf(a.x, b0.y, acc[i][1]); acc[i][2] = fmaf(a.x, b0.z, acc[i][2]); acc[i][3] = fmaf(a.x, b0.w, acc[i][3]);
+                acc[i][0] = fmaf(a.y, b1.x, acc[i][0]); acc[i][1] = fmaf(a.y, b1.y, acc[i][1]); acc[i][2] = fmaf(a.y, b1.z, acc[i][2]); acc[i][3] = fmaf(a.y, b1.w, acc[i][3]);
+                acc[i][0] = fmaf(a.z, b2.x, acc[i][0]); acc[i][1] = fmaf(a.z, b2.y, acc[i][1]); acc[i][2] = fmaf(a.z, b2.z, acc[i][2]); acc[i][3] = fmaf(a.z, b2.w, acc[i][3]);
+                acc[i][0] = fmaf(a.w, b3.x, acc[i][0]); acc[i][1] = fmaf(a.w, b3.y, acc[i][1]); acc[i][2] = fmaf(a.w, b3.z, acc[i][2]); acc[i][3] = fmaf(a.w, b3.w, acc[i][3]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    const int64_t n0 = nbase + lane * 4;
+    if (n0 < n_vecs) {
+#pragma unroll
+        for (int i = 0; i < RW; i++) {
+            const int r = warp * RW + i;
+            if (r < rows_here) {
+                const int64_t yrow = rows[g * G + (int64_t)rowtile * TM + r];
+                float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                *reinterpret_cast<float4 *>(Y + yrow * ldy + n0) = o;
+            }
+        }
+    }
+}
+
+template <int RW>
+int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int G, int K_pad,
+              const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
+{
+    constexpr int TM = 8 * RW;
+    const size_t smem = sizeof(float) * kStages * (TM * KT + KT * TN);
+    const int tiles_per_group = (G + TM - 1) / TM;
+    const int64_t gx = n_groups * tiles_per_group, gy = kn_cdiv(n_vecs, TN);
+    KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm_pg: grid too large");
+    static bool configured = false;
+    if (!configured) {
+        KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, n_groups, G, K_pad, tiles_per_group, X, ldx, Y, ldy, n_vecs);
+    else      pg_simt_kernel<RW, false><<<grid, kThreads, smem, s>>>(rows, cols, vals, n_groups, G, K_pad, tiles_per_group, X, ldx, Y, ldy, n_vecs);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
+int row_grid(int64_t n_rows) {
+    const int64_t want = kn_cdiv(n_rows, kThreads / 32);
+    const int64_t cap = (int64_t)kn_sm_count() * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+}  // namespace
+
+KN_API int kn_csr_row_pattern_hash(const int64_t *indptr, const int32_t *indices, int64_t n_rows, uint64_t *hash, void *stream) {
+    KN_REQUIRE(n_rows >= 0, "pattern_hash: negative row count");
+    if (n_rows == 0) return KN_OK;
+    KN_REQUIRE(indptr && hash, "pattern_hash: null pointer");
+    row_pattern_hash_kernel<<<row_grid(n_rows), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, n_rows, hash);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
+KN_API int kn_pg_verify(const int64_t *indptr, const int32_t *indices, const int64_t *rows, const int64_t *leaders, int64_t n,
+                        int32_t *mismatch, void *stream) {
+    KN_REQUIRE(n >= 0, "pg_verify: negative count");
+    if (n == 0) return KN_OK;
+    KN_REQUIRE(indptr && rows && leaders && mismatch, "pg_verify: null pointer");
+    pg_verify_kernel<<<row_grid(n), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, rows, leaders, n, mismatch);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
+KN_API int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data, const int64_t *rows,
+                      int64_t n_groups, int32_t G, int32_t K_pad, int32_t *cols, float *vals, void *stream) {
+    KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KT == 0, "pg_pack: bad shape (G=%d K_pad=%d)", G, K_pad);
+    if (n_groups == 0) return KN_OK;
+    KN_REQUIRE(indptr && indices && data && rows && cols && vals, "pg_pack: null pointer");
+    pg_pack_kernel<<<row_grid(n_groups * G), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, rows, n_groups, G, K_pad, cols, vals);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
+KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int32_t G, int32_t K_pad,
+                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+    KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KT == 0, "spmm_pg: bad shape (G=%d K_pad=%d)", G, K_pad);
+    KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg: bad leading dimension");
+    if (n_groups == 0 || n_vecs == 0) return KN_OK;
+    KN_REQUIRE(rows && cols && vals && X && Y, "spmm_pg: null pointer");
+    KN_REQUIRE(n_vecs % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (((uintptr_t)X | (uintptr_t)Y) & 15) == 0,
+               "spmm_pg: n_vecs, ldx, ldy must be multiples of 4 and X, Y 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool relu = (flags & KN_SPMM_RELU) != 0;
+    if (G <= 8)  return launch_pg<1>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 16) return launch_pg<2>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 32) return launch_pg<4>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 64) return launch_pg<8>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    // pick the row tile (96 or 128) that wastes fewer padded rows
+    const int waste96 = ((G + 95) / 96) * 96 - G, waste128 = ((G + 127) / 128) * 128 - G;
+    if (waste96 < waste128) return launch_pg<12>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    return launch_pg<16>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+}

@@ -44,7 +44,8 @@ template <int V, bool RELU>
 __global__ void __launch_bounds__(kWarps * 32)
 spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                     const float *__restrict__ data, int64_t n_rows,
-                    const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
+                    const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs,
+                    const int32_t *__restrict__ out_rows)
 {
     __shared__ int2 s_ent[kWarps][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +101,7 @@ spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
 #pragma unroll
             for (int i = 0; i < V; i++) acc[i] = fmaxf(acc[i], 0.0f);
         }
-        float *yp = Y + row * ldy + n0;
+        float *yp = Y + (out_rows ? (int64_t)out_rows[row] : row) * ldy + n0;
         if constexpr (V == 4) *reinterpret_cast<float4 *>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         else if constexpr (V == 2) *reinterpret_cast<float2 *>(yp) = make_float2(acc[0], acc[1]);
         else yp[0] = acc[0];
@@ -111,12 +112,14 @@ template <int NB, bool RELU>
 __global__ void __launch_bounds__(kWarps * 32)
 spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                       const float *__restrict__ data, int64_t n_rows,
-                      const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int n_vecs)
+                      const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int n_vecs,
+                      const int32_t *__restrict__ out_rows)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
     if (row >= n_rows) return;
     const int64_t beg = indptr[row], end = indptr[row + 1];
+    const int64_t yrow = out_rows ? (int64_t)out_rows[row] : row;
     float acc[NB];
 #pragma unroll
     for (int n = 0; n < NB; n++) acc[n] = 0.0f;
@@ -135,40 +138,40 @@ spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restr
     }
 #pragma unroll
     for (int n = 0; n < NB; n++)
-        if (lane == n && n < n_vecs) Y[row * ldy + n] = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
+        if (lane == n && n < n_vecs) Y[yrow * ldy + n] = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
 }
 
 template <int V>
 int launch_rowwarp(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, const int32_t *out_rows, cudaStream_t s)
 {
     const int64_t gx = kn_cdiv(n_rows, kWarps), gy = kn_cdiv(n_vecs, 32 * V);
     KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large (rows=%lld, n_vecs=%lld)", (long long)n_rows, (long long)n_vecs);
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (relu) spmm_rowwarp_kernel<V, true><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs);
-    else      spmm_rowwarp_kernel<V, false><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs);
+    if (relu) spmm_rowwarp_kernel<V, true><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
+    else      spmm_rowwarp_kernel<V, false><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
 
 template <int NB>
 int launch_lanes(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                 const float *X, int64_t ldx, float *Y, int64_t ldy, int n_vecs, bool relu, cudaStream_t s)
+                 const float *X, int64_t ldx, float *Y, int64_t ldy, int n_vecs, bool relu, const int32_t *out_rows, cudaStream_t s)
 {
     const int64_t gx = kn_cdiv(n_rows, kWarps);
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm: too many rows (%lld)", (long long)n_rows);
-    if (relu) spmm_lanes_nnz_kernel<NB, true><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs);
-    else      spmm_lanes_nnz_kernel<NB, false><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs);
+    if (relu) spmm_lanes_nnz_kernel<NB, true><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
+    else      spmm_lanes_nnz_kernel<NB, false><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
 
 }  // namespace
 
-KN_API int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *data,
-                           int64_t n_rows, int64_t n_cols,
-                           const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
-                           uint32_t flags, void *stream)
+static int spmm_csr_impl(const int64_t *indptr, const int32_t *indices, const float *data,
+                         int64_t n_rows, int64_t n_cols, const int32_t *out_rows,
+                         const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
+                         uint32_t flags, void *stream)
 {
     KN_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_vecs >= 0, "spmm: negative dimension");
     KN_REQUIRE(ldx >= n_vecs && ldy >= n_vecs, "spmm: leading dimension smaller than n_vecs (ldx=%lld ldy=%lld n_vecs=%lld)",
@@ -180,15 +183,31 @@ KN_API int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const 
     const bool relu = (flags & KN_SPMM_RELU) != 0;
     if (n_vecs <= 8) {
         const int nv = (int)n_vecs;
-        if (nv == 1) return launch_lanes<1>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, s);
-        if (nv == 2) return launch_lanes<2>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, s);
-        if (nv <= 4) return launch_lanes<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, s);
-        return launch_lanes<8>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, s);
+        if (nv == 1) return launch_lanes<1>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, out_rows, s);
+        if (nv == 2) return launch_lanes<2>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, out_rows, s);
+        if (nv <= 4) return launch_lanes<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, out_rows, s);
+        return launch_lanes<8>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, out_rows, s);
     }
     const uintptr_t align = (uintptr_t)X | (uintptr_t)Y;
     if (n_vecs % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (align & 15) == 0 && n_vecs >= 128)
-        return launch_rowwarp<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, s);
+        return launch_rowwarp<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
     if (n_vecs % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && (align & 7) == 0 && n_vecs >= 64)
-        return launch_rowwarp<2>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, s);
-    return launch_rowwarp<1>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, s);
+        return launch_rowwarp<2>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
+    return launch_rowwarp<1>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
+}
+
+KN_API int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *data,
+                           int64_t n_rows, int64_t n_cols,
+                           const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
+                           uint32_t flags, void *stream)
+{
+    return spmm_csr_impl(indptr, indices, data, n_rows, n_cols, nullptr, X, ldx, Y, ldy, n_vecs, flags, stream);
+}
+
+KN_API int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const float *data,
+                                int64_t n_rows, int64_t n_cols, const int32_t *out_rows,
+                                const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
+                                uint32_t flags, void *stream)
+{
+    return spmm_csr_impl(indptr, indices, data, n_rows, n_cols, out_rows, X, ldx, Y, ldy, n_vecs, flags, stream);
 }

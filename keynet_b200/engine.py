@@ -32,7 +32,7 @@ class ForwardPlan(object):
         self.acts = [torch.empty((W.shape[0], N), dtype=torch.float32, device=self.dev) for (_, W, _) in self.layers]
         self.logits = torch.empty((N, self.K), dtype=torch.float32, device=self.dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.launches_per_run = 2 + len(self.layers)
+        self.launches_per_run = 2 + sum((W._pg.launches() if (W._pg is not None and N >= 32 and N % 4 == 0) else 1) for (_, W, _) in self.layers)
         self.time_layers = time_layers
         # per-layer CUDA events on the launch stream, one set per timed step (read back after the timed region)
         self.layer_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.layers]

@@ -76,6 +76,8 @@ class KeyedLayer(nn.Module):
         else:
             raise ValueError('unsupported layer type "%s"' % str(type(module)))
 
+        if tileshape is None:
+            self.W.optimize()          # pattern-grouped execution format for batched forward (csrc/pgroup.cu)
         if tileshape is not None:
             from .tiled import tile_keyed_layer
             self.W = tile_keyed_layer(self.W, module, inshape, outshape, tileshape)

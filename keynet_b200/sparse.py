@@ -217,6 +217,7 @@ class SparseMatrix(object):
     def __init__(self, A=None, device=None):
         self.ndim = 2
         self.dtype = np.float32
+        self._pg = None          # optional pattern-grouped execution format (PatternGroups)
         if A is None:
             (self.shape, self._indptr, self._indices, self._data) = ((0, 0), None, None, None)
             return
@@ -366,11 +367,128 @@ class SparseMatrix(object):
         D[np.repeat(np.arange(self.shape[0]), np.diff(ip)), ix] = dt
         return D
 
+    def optimize(self, min_group=4, min_nnz=4096):
+        """Build the pattern-grouped execution format (csrc/pgroup.cu) next to the canonical CSR.  The CSR stays
+        the source of truth (parity, export, small batches); batches of >= 32 images run on the groups."""
+        if self._pg is None and self.nnz() >= min_nnz:
+            self._pg = PatternGroups.build(self, min_group=min_group)
+        return self
+
     def row_slice(self, r0, r1):
         """Rows [r0, r1) as a view-like SparseMatrix sharing indices/data (indptr offsets stay absolute)."""
         M = SparseMatrix()
         (M.shape, M._indptr, M._indices, M._data) = ((r1 - r0, self.shape[1]), self._indptr[r0:r1 + 1], self._indices, self._data)
         return M
+
+
+# =============================================================================================
+# Pattern-grouped execution format
+# =============================================================================================
+class PatternGroups(object):
+    """Rows with an identical column set, packed as dense value blocks (see csrc/pgroup.cu).
+
+    classes: list of dict(G, K_pad, n_groups, rows int32[n_groups*G], cols int32[n_groups*K_pad], vals f32[n_groups*G*K_pad])
+    rest:    rows not covered by a group, as a compact CSR + out_rows int32 (None if every row is grouped)
+    Grouping / sorting uses torch device ops (build-time plumbing); hashing, verification, packing and the
+    product itself are kernels of libkeynet_b200."""
+
+    def __init__(self):
+        self.classes = []
+        self.rest = None
+        self.shape = None
+        self.grouped_rows = 0
+        self.padded_values = 0
+
+    @staticmethod
+    def build(W, min_group=4, max_pad_waste=0.25):
+        L = _native.lib()
+        dev = W._data.device
+        (R, C) = W.shape
+        pg = PatternGroups()
+        pg.shape = W.shape
+        (indptr, indices, data) = (W._indptr, W._indices, W._data)
+        if indptr[0].item() != 0:                      # row-slice view: rebase offsets
+            (indices, data) = (indices[indptr[0]:indptr[-1]], data[indptr[0]:indptr[-1]])
+            indptr = indptr - indptr[0]
+        h = torch.empty(R, dtype=torch.int64, device=dev)
+        check(L.kn_csr_row_pattern_hash(ptr(indptr), ptr(indices), R, ptr(h), stream_ptr()))
+        (hs, order) = torch.sort(h)
+        new = torch.ones(R, dtype=torch.bool, device=dev)
+        new[1:] = hs[1:] != hs[:-1]
+        gid = torch.cumsum(new.to(torch.int64), 0) - 1
+        start = torch.nonzero(new).reshape(-1)                       # first position of every group in `order`
+        gsize = torch.diff(torch.cat([start, torch.tensor([R], device=dev)]))
+        leader = order[start]
+        # a 64-bit hash collision would merge different patterns: verify every row against its group leader
+        mismatch = torch.empty(R, dtype=torch.int32, device=dev)
+        check(L.kn_pg_verify(ptr(indptr), ptr(indices), ptr(order), ptr(leader[gid].contiguous()), R, ptr(mismatch), stream_ptr()))
+        if bool(mismatch.any()):
+            warnings.warn('pattern hash collision: matrix stays on the CSR kernel')
+            return None
+        nnz_row = indptr[1:] - indptr[:-1]
+        K = nnz_row[leader]
+        first_col = torch.where(K > 0, indices[indptr[leader].clamp(max=max(indices.numel() - 1, 0))].to(torch.int64), torch.full_like(K, C))
+        sel = (gsize >= min_group) & (K > 0)
+        in_group = torch.zeros(R, dtype=torch.bool, device=dev)
+        for G in torch.unique(gsize[sel]).tolist():
+            gi = torch.nonzero(sel & (gsize == G)).reshape(-1)
+            # split the class where padding every group to the widest one would waste too much
+            Ks = K[gi]
+            (Ks_sorted, o) = torch.sort(Ks, descending=True)
+            gi = gi[o]
+            bounds = [0]
+            Kl = Ks_sorted.tolist()
+            for (j, k) in enumerate(Kl):
+                if k < (1.0 - max_pad_waste) * Kl[bounds[-1]]:
+                    bounds.append(j)
+            bounds.append(len(Kl))
+            for (b0, b1) in zip(bounds[:-1], bounds[1:]):
+                g_sub = gi[b0:b1]
+                g_sub = g_sub[torch.argsort(first_col[g_sub])]       # neighbouring CTAs gather neighbouring X rows
+                K_pad = int((Kl[b0] + 31) // 32 * 32)
+                ng = int(g_sub.numel())
+                pos = (start[g_sub].reshape(-1, 1) + torch.arange(G, device=dev).reshape(1, -1)).reshape(-1)
+                rows64 = order[pos].contiguous()
+                # ascending row ids inside a group: deterministic output layout
+                rows64 = torch.sort(rows64.reshape(ng, G), dim=1)[0].reshape(-1).contiguous()
+                cols = torch.empty(ng * K_pad, dtype=torch.int32, device=dev)
+                vals = torch.empty(ng * G * K_pad, dtype=torch.float32, device=dev)
+                check(L.kn_pg_pack(ptr(indptr), ptr(indices), ptr(data), ptr(rows64), ng, int(G), K_pad, ptr(cols), ptr(vals), stream_ptr()))
+                pg.classes.append(dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals))
+                in_group[rows64] = True
+                pg.grouped_rows += ng * int(G)
+                pg.padded_values += ng * int(G) * K_pad
+        rest_rows = torch.nonzero(~in_group).reshape(-1)
+        if rest_rows.numel() > 0:
+            n = int(rest_rows.numel())
+            csr = _two_phase(
+                n,
+                lambda row_nnz: check(L.kn_csr_gather_rows_count(ptr(indptr), ptr(rest_rows), n, ptr(row_nnz), stream_ptr())),
+                lambda ip, ix, dt: check(L.kn_csr_gather_rows_fill(ptr(indptr), ptr(indices), ptr(data), ptr(rest_rows), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+                dev)
+            pg.rest = dict(n=n, indptr=csr[0], indices=csr[1], data=csr[2], out_rows=rest_rows.to(torch.int32))
+        if len(pg.classes) == 0:
+            return None
+        return pg
+
+    def spmm(self, x, y, relu):
+        L = _native.lib()
+        N = x.shape[1]
+        flags = _native.KN_SPMM_RELU if relu else 0
+        for c in self.classes:
+            check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), c['n_groups'], c['G'], c['K_pad'],
+                                   ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+        r = self.rest
+        if r is not None:
+            check(L.kn_spmm_csr_rows_f32(ptr(r['indptr']), ptr(r['indices']), ptr(r['data']), r['n'], self.shape[1], ptr(r['out_rows']),
+                                         ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+
+    def launches(self):
+        return len(self.classes) + (1 if self.rest is not None else 0)
+
+    def summary(self):
+        return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], grouped_rows=self.grouped_rows,
+                    rest_rows=0 if self.rest is None else self.rest['n'], padded_values=self.padded_values)
 
 
 # =============================================================================================
@@ -383,6 +501,9 @@ def spmm(W, x, relu=False, out=None):
     (R, N) = (W.shape[0], x.shape[1])
     y = out if out is not None else torch.empty((R, N), dtype=torch.float32, device=x.device)
     assert y.shape == (R, N) and y.is_contiguous()
+    if W._pg is not None and N >= 32 and N % 4 == 0:
+        W._pg.spmm(x, y, relu)
+        return y
     check(_native.lib().kn_spmm_csr_f32(ptr(W._indptr), ptr(W._indices), ptr(W._data), R, W.shape[1],
                                         ptr(x), N, ptr(y), N, N, _native.KN_SPMM_RELU if relu else 0, stream_ptr()))
     return y

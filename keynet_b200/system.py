@@ -209,7 +209,7 @@ class KeyedSensor(_layer.KeyedLayer):
         The homogeneous coordinate and the batch-major -> feature-major transpose are one fused kernel."""
         assert self.isloaded(), "Load image first"
         if not self.isencrypted():
-            x = self.tensor()
+            x = KeyedSensor.tensor(self)
             on_host = not x.is_cuda
             dev = torch.device('cuda', torch.cuda.current_device())
             xd = x.to(dev, non_blocking=True).contiguous()

@@ -365,3 +365,62 @@ def test_keyed_relu_after_batchnorm_and_merge():
     yp = net(x).detach().numpy()
     assert np.allclose(y, yp, atol=1e-4), np.abs(y - yp).max()
     assert np.array_equal(y.argmax(1), yp.argmax(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# Pattern-grouped execution format (csrc/pgroup.cu)
+@pytest.mark.parametrize('case', ['conv_perm_gain', 'conv_identity_s2', 'linear', 'pool'])
+@pytest.mark.parametrize('N', [32, 100, 128, 516])
+def test_pattern_groups_match_csr_and_oracle(case, N):
+    from keynet_b200 import sparse
+    ko = _ko()
+    rs = np.random.RandomState(17)
+
+    def key(n, permute, gain):
+        perm = np.concatenate([rs.permutation(n - 1), [n - 1]]) if permute else np.arange(n)
+        scale = np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32) if gain else np.ones(n, dtype=np.float32)
+        return sparse.MonomialKey(perm, scale)
+    if case == 'conv_perm_gain':
+        (C, U, V, M) = (5, 10, 12, 24)
+        W = sparse.keyed_toeplitz_conv2d((C, U, V), rs.randn(M, C, 3, 3).astype(np.float32), rs.randn(M).astype(np.float32), 1,
+                                         key(M * U * V + 1, True, True), key(C * U * V + 1, True, True).transpose())
+        expect_G = {M}
+    elif case == 'conv_identity_s2':
+        (C, U, V, M) = (3, 16, 16, 100)
+        W = sparse.keyed_toeplitz_conv2d((C, U, V), rs.randn(M, C, 3, 3).astype(np.float32), rs.randn(M).astype(np.float32), 2,
+                                         None, sparse.sparse_identity_matrix(C * U * V + 1))
+        expect_G = {M}
+    elif case == 'linear':
+        W = sparse.keyed_linear(torch.from_numpy(rs.randn(70, 333).astype(np.float32)), torch.from_numpy(rs.randn(70).astype(np.float32)),
+                                key(71, True, False), key(334, True, True).transpose())
+        expect_G = {70}
+    else:
+        W = sparse.keyed_toeplitz_avgpool2d((6, 12, 12), 3, 2, key(6 * 36 + 1, True, False), key(6 * 144 + 1, True, False).transpose())
+        expect_G = set()
+    (ip, ix, dt) = W.csr_arrays()
+    A = ko.csr(W.shape, ip, ix, dt)
+    X = rs.randn(W.shape[1], N).astype(np.float32)
+    X[-1] = 1.0                                      # homogeneous coordinate
+    Xd = torch.from_numpy(X).cuda()
+    W._pg = None
+    y_csr = sparse.spmm(W, Xd, relu=True).cpu().numpy()
+    W._pg = sparse.PatternGroups.build(W, min_group=4)
+    if not expect_G:
+        assert W._pg is None                         # pool rows all have distinct patterns: stays CSR
+        return
+    assert W._pg is not None and {c['G'] for c in W._pg.classes} == expect_G
+    s = W._pg.summary()
+    assert s['grouped_rows'] + s['rest_rows'] == W.shape[0]
+    y_pg = sparse.spmm(W, Xd, relu=True).cpu().numpy()
+    ref = ko.spmm(A, X, relu=True, threads=4)
+    assert _close(y_pg, ref), np.abs(y_pg - ref).max()
+    assert _close(y_pg, y_csr)
+    assert bool((y_pg[-1] == 1.0).all())             # homogeneous row (rest CSR) stays exactly one
+
+
+def test_pattern_groups_absent_for_unstructured_matrix():
+    from keynet_b200 import sparse
+    rs = np.random.RandomState(5)
+    A = _rand_csr(rs, 300, 400, 0.05)
+    W = sparse.SparseMatrix((A.shape, A.indptr, A.indices, A.data))
+    assert sparse.PatternGroups.build(W) is None
