@@ -12,6 +12,8 @@ Representation choices (B200-first, not a port):
     there: Toeplitz rows are written in closed form (csrc/toeplitz.cu), keys are folded in by
     csrc/keycompile.cu.
 """
+import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -384,6 +386,17 @@ class SparseMatrix(object):
 # =============================================================================================
 # Pattern-grouped execution format
 # =============================================================================================
+_TC = {'enabled': os.environ.get('KEYNET_B200_TENSOR_CORES', '1') != '0'}
+
+
+def tensor_cores_enabled(flag=None):
+    """Switch for the tcgen05 path of pattern groups (default on; KEYNET_B200_TENSOR_CORES=0 or
+    tensor_cores_enabled(False) keeps everything on the fp32 FMA kernels)."""
+    if flag is not None:
+        _TC['enabled'] = bool(flag)
+    return _TC['enabled']
+
+
 class PatternGroups(object):
     """Rows with an identical column set, packed as dense value blocks (see csrc/pgroup.cu).
 
@@ -391,6 +404,9 @@ class PatternGroups(object):
     rest:    rows not covered by a group, as a compact CSR + out_rows int32 (None if every row is grouped)
     Grouping / sorting uses torch device ops (build-time plumbing); hashing, verification, packing and the
     product itself are kernels of libkeynet_b200."""
+
+    TC_MIN_G = 32          # groups at least this tall are "true small GEMMs": tcgen05 path
+    TC_MIN_BATCH = 128
 
     def __init__(self):
         self.classes = []
@@ -454,7 +470,15 @@ class PatternGroups(object):
                 cols = torch.empty(ng * K_pad, dtype=torch.int32, device=dev)
                 vals = torch.empty(ng * G * K_pad, dtype=torch.float32, device=dev)
                 check(L.kn_pg_pack(ptr(indptr), ptr(indices), ptr(data), ptr(rows64), ng, int(G), K_pad, ptr(cols), ptr(vals), stream_ptr()))
-                pg.classes.append(dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals))
+                cls = dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals, tc=None)
+                if int(G) >= PatternGroups.TC_MIN_G and tensor_cores_enabled():
+                    # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
+                    (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
+                    check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
+                    maps = ctypes.create_string_buffer(2 * 128)
+                    check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), ng * int(G), int(G), K_pad, maps))
+                    cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
+                pg.classes.append(cls)
                 in_group[rows64] = True
                 pg.grouped_rows += ng * int(G)
                 pg.padded_values += ng * int(G) * K_pad
@@ -476,8 +500,12 @@ class PatternGroups(object):
         N = x.shape[1]
         flags = _native.KN_SPMM_RELU if relu else 0
         for c in self.classes:
-            check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), c['n_groups'], c['G'], c['K_pad'],
-                                   ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+            if c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
+                check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), c['n_groups'], c['G'], c['K_pad'],
+                                          ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+            else:
+                check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), c['n_groups'], c['G'], c['K_pad'],
+                                       ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
         r = self.rest
         if r is not None:
             check(L.kn_spmm_csr_rows_f32(ptr(r['indptr']), ptr(r['indices']), ptr(r['data']), r['n'], self.shape[1], ptr(r['out_rows']),
@@ -487,7 +515,7 @@ class PatternGroups(object):
         return len(self.classes) + (1 if self.rest is not None else 0)
 
     def summary(self):
-        return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], grouped_rows=self.grouped_rows,
+        return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], tensor_core=[c['tc'] is not None for c in self.classes], grouped_rows=self.grouped_rows,
                     rest_rows=0 if self.rest is None else self.rest['n'], padded_values=self.padded_values)
 
 

@@ -424,3 +424,39 @@ def test_pattern_groups_absent_for_unstructured_matrix():
     A = _rand_csr(rs, 300, 400, 0.05)
     W = sparse.SparseMatrix((A.shape, A.indptr, A.indices, A.data))
     assert sparse.PatternGroups.build(W) is None
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 (3xTF32) path of the pattern groups (csrc/pgroup_tc.cu)
+@pytest.mark.parametrize('M,C,N', [(32, 3, 128), (96, 4, 256), (192, 2, 516), (100, 3, 384), (24, 5, 128), (512, 1, 260), (96, 20, 4096)])
+def test_pattern_groups_tensor_core_path(M, C, N):
+    """Same matrix through the fp32 CSR kernel, the fp32 grouped kernel and the tcgen05 kernel: all within
+    rtol 1e-4 of the oracle (3xTF32 keeps ~fp32 accuracy; plain TF32 would not)."""
+    from keynet_b200 import sparse
+    ko = _ko()
+    rs = np.random.RandomState(M + N)
+    (U, V) = (6, 8)
+    perm_gain = lambda n: sparse.MonomialKey(np.concatenate([rs.permutation(n - 1), [n - 1]]), np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32))
+    sparse.tensor_cores_enabled(True)
+    W = sparse.keyed_toeplitz_conv2d((C, U, V), rs.randn(M, C, 3, 3).astype(np.float32), rs.randn(M).astype(np.float32), 1,
+                                     perm_gain(M * U * V + 1), perm_gain(C * U * V + 1).transpose())
+    W._pg = sparse.PatternGroups.build(W, min_group=4)
+    assert W._pg is not None
+    uses_tc = [c['tc'] is not None for c in W._pg.classes]
+    assert all(uses_tc) == (M >= sparse.PatternGroups.TC_MIN_G)
+    (ip, ix, dt) = W.csr_arrays()
+    X = (rs.randn(W.shape[1], N) * rs.choice([1e-3, 1.0, 50.0], size=(W.shape[1], 1))).astype(np.float32)
+    X[-1] = 1.0
+    Xd = torch.from_numpy(X).cuda()
+    ref = ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=True, threads=8)
+    y_tc = sparse.spmm(W, Xd, relu=True).cpu().numpy()
+    sparse.tensor_cores_enabled(False)
+    try:
+        y_simt = sparse.spmm(W, Xd, relu=True).cpu().numpy()
+    finally:
+        sparse.tensor_cores_enabled(True)
+    assert _close(y_simt, ref), np.abs(y_simt - ref).max()
+    assert _close(y_tc, ref), (np.abs(y_tc - ref).max(), np.abs(ref).max())
+    # no ReLU variant
+    y2 = sparse.spmm(W, Xd, relu=False).cpu().numpy()
+    assert _close(y2, ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=False, threads=8))
