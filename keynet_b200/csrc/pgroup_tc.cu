@@ -13,8 +13,9 @@
 //     TF32) and lo = v - hi, stored K-contiguous, loaded by TMA (SWIZZLE_64B boxes of 16 k x Gp rows).
 //   * A = gathered activation rows X[cols[g][k], n0:n0+128]: four producer warps read each 512-byte row
 //     segment with coalesced LDG.128, split it into hi/lo in registers and store both into the UMMA
-//     canonical MN-major SWIZZLE_128B layout (atom = 32 batch x 8 k, 16-byte chunk j of row k lands at
-//     chunk j ^ (k & 7)), then fence.proxy.async + mbarrier arrive.
+//     canonical MN-major SWIZZLE_128B_BASE32B layout -- the only MN-major layout tcgen05 accepts for 32-bit
+//     operands (atom = 32 batch x 4 k = 512 B, 32-byte chunk c of row k lands at chunk c ^ (k & 3)) -- then
+//     fence.proxy.async + mbarrier arrive.
 //   * one elected thread issues, per 8-k step, hi.hi + lo.hi + hi.lo (fp32 accumulate in TMEM): the
 //     dropped lo.lo term is below 2^-22 relative, so results stay inside the fp32 rtol 1e-4 parity bar,
 //     which plain TF32 (10-bit mantissa) would not.
@@ -81,7 +82,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
 }
-constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
+constexpr uint32_t kLayoutSW128B32 = 1, kLayoutSW64 = 4;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, A MN-major, B K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -98,7 +99,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment for the swizzle atoms
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int a_tile_bytes = 2 * 4 * 1024;                       // [kgroup 2][m 4][1024] per batch tile, hi or lo
+    const int a_tile_bytes = 4 * 4 * 512;                        // [k-atom 4][batch-atom 4][512] per batch tile, hi or lo
     const int a_stage_bytes = NB * 2 * a_tile_bytes;             // NB batch tiles x (hi, lo)
     const int b_plane_bytes = Gp * KS * 4;                       // Gp rows x 64 B
     const int stage_bytes = a_stage_bytes + 2 * b_plane_bytes;
@@ -157,9 +158,10 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                     const uint32_t a_hi = sa + b * 2 * a_tile_bytes, a_lo = a_hi + a_tile_bytes;
 #pragma unroll
                     for (int kk = 0; kk < KS / 8; kk++) {
-                        // A: MN-major SW128, LBO = 1024 (next 32 batch columns), SBO = 4096 (next 8 k)
-                        const uint64_t da_hi = make_desc(a_hi + kk * 4096, 1024, 4096, kLayoutSW128);
-                        const uint64_t da_lo = make_desc(a_lo + kk * 4096, 1024, 4096, kLayoutSW128);
+                        // A: MN-major SWIZZLE_128B_BASE32B (the only MN-major layout for 32-bit operands): atom = 32 batch x 4 k
+                        // (512 B), LBO = 512 (next 32 batch columns), SBO = 2048 (next 4 k); one MMA (8 k) spans two k-atoms
+                        const uint64_t da_hi = make_desc(a_hi + kk * 4096, 512, 2048, kLayoutSW128B32);
+                        const uint64_t da_lo = make_desc(a_lo + kk * 4096, 512, 2048, kLayoutSW128B32);
                         // B: K-major SW64 (64-byte rows), 8-row groups 512 B apart; second k step = +32 B
                         const uint64_t db_hi = make_desc(sb + kk * 32, 16, 512, kLayoutSW64);
                         const uint64_t db_lo = make_desc(sb + b_plane_bytes + kk * 32, 16, 512, kLayoutSW64);
@@ -200,8 +202,8 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int k = rsub + 4 * i;
-                const int kg = k >> 3, k8 = k & 7;
-                const int off = kg * 4096 + m_atom * 1024 + k8 * 128 + ((j ^ k8) << 4);
+                const int k4 = k & 3;
+                const int off = (k >> 2) * 2048 + m_atom * 512 + k4 * 128 + ((((j >> 1) ^ k4) << 5) | ((j & 1) << 4));
 #pragma unroll
                 for (int b = 0; b < NB; b++) {
                     const float4 x = v[b][i];
