@@ -72,13 +72,14 @@ int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const fl
  *   kn_pg_verify             mismatch[i]=1 iff rows[i] and leaders[i] differ in their column lists
  *   kn_pg_pack               rows[n_groups][G] -> cols[n_groups][K_pad], vals[n_groups][G][K_pad] (zero padded)
  *   kn_spmm_pg_f32           Y[rows[g][:], :] = vals[g] . X[cols[g][:], :]  (+ReLU); fp32 FMA, K_pad % 32 == 0,
- *                            n_vecs/ldx/ldy multiples of 4 */
+ *                            n_vecs/ldx/ldy multiples of 4; group_k[g] (nullable) = number of leading columns of group g
+ *                            that are real (the rest of K_pad is zero padding and is skipped) */
 int kn_csr_row_pattern_hash(const int64_t *indptr, const int32_t *indices, int64_t n_rows, uint64_t *hash, void *stream);
 int kn_pg_verify(const int64_t *indptr, const int32_t *indices, const int64_t *rows, const int64_t *leaders, int64_t n,
                  int32_t *mismatch, void *stream);
 int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data, const int64_t *rows,
                int64_t n_groups, int32_t G, int32_t K_pad, int32_t *cols, float *vals, void *stream);
-int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int32_t G, int32_t K_pad,
+int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
 /* Tensor-core variant (csrc/pgroup_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo),
@@ -89,7 +90,7 @@ int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, 
 #define KN_TENSORMAP_BYTES 128
 int kn_pg_tc_split(const float *vals, int64_t n, float *vals_hi, float *vals_lo, void *stream);
 int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64_t n_rows_total, int32_t G, int32_t K_pad, void *maps_out_host);
-int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, int64_t n_groups, int32_t G, int32_t K_pad,
+int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
                       const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
 /* ---- prefix sum: out[0]=0, out[i+1]=out[i]+in[i]; out has n+1 entries (in may alias out+1) */
@@ -137,11 +138,13 @@ int kn_linear_fill(const float *weight, const float *bias, int64_t n_out, int64_
  *     v' = fl32( fl32(row_scale[r]*v) * col_scale[c] )     (left product first, as the reference)
  *     dropped if v' == 0                      (scipy SpGEMM drops exact zeros)
  * and writes rows with ascending c' (canonical form).  col_map / row_scale / col_scale may be
- * NULL (identity / 1.0).  No FMA contraction, no flush-to-zero: values are bit-exact with scipy. */
+ * NULL (identity / 1.0).  No FMA contraction, no flush-to-zero: values are bit-exact with scipy.
+ * keep_zeros != 0 keeps exact zeros (the structural matrix the pattern groups are built from, so that a tiny weight
+ * rounded to 0 by the reference's offset trick does not split a pixel's rows into different column patterns). */
 int kn_keycompile_count(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                        const float *row_scale, const float *col_scale, int64_t *row_nnz, void *stream);
+                        const float *row_scale, const float *col_scale, int32_t keep_zeros, int64_t *row_nnz, void *stream);
 int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows, int64_t n_cols,
-                       const int32_t *col_map, const float *row_scale, const float *col_scale,
+                       const int32_t *col_map, const float *row_scale, const float *col_scale, int32_t keep_zeros,
                        const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
 
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left

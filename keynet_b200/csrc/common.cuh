@@ -52,3 +52,21 @@ __device__ __forceinline__ float kn_ldg_stream_f32(const float *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+
+// CTA rasterisation shared by the grouped kernels: a 1-D grid enumerates (work item, batch tile) pairs so that
+// the batch tiles of one work item (pattern group / row tile) run back to back inside a super-tile of `S` batch
+// tiles -- its weight block is fetched from HBM once per super-tile and then served from L2 -- while the X rows
+// touched by neighbouring work items of the same super-tile (S*tile columns wide) stay L2-resident as well.
+struct KnRaster { int64_t item; int64_t tile; };
+__device__ __forceinline__ KnRaster kn_raster(int64_t linear, int64_t n_items, int64_t n_tiles, int64_t S) {
+    const int64_t full = n_tiles / S, rem = n_tiles - full * S, per_super = S * n_items;
+    KnRaster r;
+    if (linear < full * per_super) {
+        const int64_t sup = linear / per_super, w = linear - sup * per_super;
+        r.item = w / S; r.tile = sup * S + (w - r.item * S);
+    } else {
+        const int64_t w = linear - full * per_super;
+        r.item = w / rem; r.tile = full * S + (w - r.item * rem);
+    }
+    return r;
+}

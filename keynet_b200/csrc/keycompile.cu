@@ -36,7 +36,7 @@ __device__ __forceinline__ float keyed_value(float v, const float *row_scale, co
 __global__ void __launch_bounds__(kThreads)
 keycompile_count_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
                         int64_t n_rows, const float *__restrict__ row_scale, const float *__restrict__ col_scale,
-                        int64_t *__restrict__ row_nnz)
+                        int keep_zeros, int64_t *__restrict__ row_nnz)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = kThreads / 32;
@@ -44,7 +44,7 @@ keycompile_count_kernel(const int64_t *__restrict__ indptr, const int32_t *__res
         const int64_t beg = indptr[r], end = indptr[r + 1];
         int cnt = 0;
         for (int64_t e = beg + lane; e < end; e += 32)
-            cnt += (keyed_value(data[e], row_scale, col_scale, r, indices[e]) != 0.0f) ? 1 : 0;
+            cnt += (keep_zeros || keyed_value(data[e], row_scale, col_scale, r, indices[e]) != 0.0f) ? 1 : 0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
         if (lane == 0) row_nnz[r] = cnt;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void bitonic_sort_pairs(KeyPtr keys, ValPtr vals, int
 __global__ void __launch_bounds__(kThreads)
 keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
                        int64_t n_rows, int64_t n_cols, const int32_t *__restrict__ col_map,
-                       const float *__restrict__ row_scale, const float *__restrict__ col_scale,
+                       const float *__restrict__ row_scale, const float *__restrict__ col_scale, int keep_zeros,
                        const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -107,7 +107,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
             __syncthreads();
             for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
                 const int32_t c = indices[e];
-                if (keyed_value(data[e], row_scale, col_scale, r, c) != 0.0f) {
+                if (keep_zeros || keyed_value(data[e], row_scale, col_scale, r, c) != 0.0f) {
                     const int32_t cn = col_map ? col_map[c] : c;
                     atomicOr(&s_bits[cn >> 5], 1u << (cn & 31));
                 }
@@ -129,7 +129,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
             for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
                 const int32_t c = indices[e];
                 const float v = keyed_value(data[e], row_scale, col_scale, r, c);
-                if (v != 0.0f) {
+                if (keep_zeros || v != 0.0f) {
                     const int32_t cn = col_map ? col_map[c] : c;
                     const int pos = s_pref[cn >> 5] + __popc(s_bits[cn >> 5] & ((1u << (cn & 31)) - 1u));
                     out_indices[obeg + pos] = cn; out_data[obeg + pos] = v;
@@ -143,7 +143,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
         for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
             const int32_t c = indices[e];
             const float v = keyed_value(data[e], row_scale, col_scale, r, c);
-            if (v != 0.0f) {
+            if (keep_zeros || v != 0.0f) {
                 const int pos = atomicAdd(&s_count, 1);         // order is irrelevant: sorted next
                 const int32_t cn = col_map ? col_map[c] : c;
                 if (in_smem) { s_key[pos] = cn; s_val[pos] = v; }
@@ -192,17 +192,17 @@ int row_grid(int64_t n_rows, int rows_per_cta) {
 }  // namespace
 
 KN_API int kn_keycompile_count(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                               const float *row_scale, const float *col_scale, int64_t *row_nnz, void *stream) {
+                               const float *row_scale, const float *col_scale, int32_t keep_zeros, int64_t *row_nnz, void *stream) {
     KN_REQUIRE(n_rows >= 0, "keycompile: negative row count");
     if (n_rows == 0) return KN_OK;
     KN_REQUIRE(indptr && indices && data && row_nnz, "keycompile: null pointer");
-    keycompile_count_kernel<<<row_grid(n_rows, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, row_scale, col_scale, row_nnz);
+    keycompile_count_kernel<<<row_grid(n_rows, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, row_scale, col_scale, keep_zeros, row_nnz);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
 
 KN_API int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows, int64_t n_cols,
-                              const int32_t *col_map, const float *row_scale, const float *col_scale,
+                              const int32_t *col_map, const float *row_scale, const float *col_scale, int32_t keep_zeros,
                               const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream) {
     KN_REQUIRE(n_rows >= 0, "keycompile: negative row count");
     if (n_rows == 0) return KN_OK;
@@ -214,7 +214,7 @@ KN_API int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, con
         KN_CUDA(cudaFuncSetAttribute(keycompile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    keycompile_fill_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, n_cols, col_map, row_scale, col_scale,
+    keycompile_fill_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, n_cols, col_map, row_scale, col_scale, keep_zeros,
                                                                                          out_indptr, out_indices, out_data);
     KN_CHECK_LAUNCH();
     return KN_OK;

@@ -102,7 +102,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int RW, bool RELU>
 __global__ void __launch_bounds__(kThreads, 2)
 pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
-               int64_t n_groups, int G, int K_pad, int tiles_per_group,
+               const int32_t *__restrict__ group_k, int64_t n_groups, int G, int K_pad, int tiles_per_group, int64_t n_items, int64_t n_tiles,
                const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
 {
     constexpr int TM = 8 * RW;
@@ -111,10 +111,12 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
     float (*sB)[KT][TN] = reinterpret_cast<float (*)[KT][TN]>(smem_raw + sizeof(float) * kStages * TM * KT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t g = blockIdx.x / tiles_per_group;
-    const int rowtile = (int)(blockIdx.x - g * tiles_per_group);
-    const int64_t nbase = (int64_t)blockIdx.y * TN;
-    const int n_chunks = K_pad / KT;
+    const KnRaster rt = kn_raster(blockIdx.x, n_items, n_tiles, 16);      // super-tile = 16 x 128 batch columns
+    const int64_t g = rt.item / tiles_per_group;
+    const int rowtile = (int)(rt.item - g * tiles_per_group);
+    const int64_t nbase = rt.tile * TN;
+    // groups of one class share K_pad (storage) but loop only over their own K (edge / corner pixels have fewer taps)
+    const int n_chunks = group_k ? (__ldg(group_k + g) + KT - 1) / KT : K_pad / KT;
 
     const float *__restrict__ vbase = vals + (g * G + (int64_t)rowtile * TM) * K_pad;
     const int32_t *__restrict__ cbase = cols + g * (int64_t)K_pad;
@@ -195,23 +197,23 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
 }
 
 template <int RW>
-int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int G, int K_pad,
+int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
     constexpr int TM = 8 * RW;
     const size_t smem = sizeof(float) * kStages * (TM * KT + KT * TN);
     const int tiles_per_group = (G + TM - 1) / TM;
     const int64_t gx = n_groups * tiles_per_group, gy = kn_cdiv(n_vecs, TN);
-    KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm_pg: grid too large");
+    KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg: grid too large");
     static bool configured = false;
     if (!configured) {
         KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, n_groups, G, K_pad, tiles_per_group, X, ldx, Y, ldy, n_vecs);
-    else      pg_simt_kernel<RW, false><<<grid, kThreads, smem, s>>>(rows, cols, vals, n_groups, G, K_pad, tiles_per_group, X, ldx, Y, ldy, n_vecs);
+    dim3 grid((unsigned)(gx * gy));
+    if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
+    else      pg_simt_kernel<RW, false><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -252,7 +254,7 @@ KN_API int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float
     return KN_OK;
 }
 
-KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, int64_t n_groups, int32_t G, int32_t K_pad,
+KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
                           const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KT == 0, "spmm_pg: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg: bad leading dimension");
@@ -262,12 +264,12 @@ KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float 
                "spmm_pg: n_vecs, ldx, ldy must be multiples of 4 and X, Y 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const bool relu = (flags & KN_SPMM_RELU) != 0;
-    if (G <= 8)  return launch_pg<1>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 16) return launch_pg<2>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 32) return launch_pg<4>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 64) return launch_pg<8>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 8)  return launch_pg<1>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 16) return launch_pg<2>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 32) return launch_pg<4>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 64) return launch_pg<8>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     // pick the row tile (96 or 128) that wastes fewer padded rows
     const int waste96 = ((G + 95) / 96) * 96 - G, waste128 = ((G + 127) / 128) * 128 - G;
-    if (waste96 < waste128) return launch_pg<12>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    return launch_pg<16>(rows, cols, vals, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (waste96 < waste128) return launch_pg<12>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    return launch_pg<16>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
 }

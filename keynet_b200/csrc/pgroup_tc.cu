@@ -11,11 +11,12 @@
 //
 //   * B = weight block V_g: pre-split at pack time into hi = v & 0xffffe000 (exactly representable in
 //     TF32) and lo = v - hi, stored K-contiguous, loaded by TMA (SWIZZLE_64B boxes of 16 k x Gp rows).
-//   * A = gathered activation rows X[cols[g][k], n0:n0+128]: four producer warps read each 512-byte row
-//     segment with coalesced LDG.128, split it into hi/lo in registers and store both into the UMMA
-//     canonical MN-major SWIZZLE_128B_BASE32B layout -- the only MN-major layout tcgen05 accepts for 32-bit
-//     operands (atom = 32 batch x 4 k = 512 B, 32-byte chunk c of row k lands at chunk c ^ (k & 3)) -- then
-//     fence.proxy.async + mbarrier arrive.
+//   * A = gathered activation rows X[cols[g][k], n0:n0+128], kept in TENSOR MEMORY (lane = batch element,
+//     column = k): eight producer warps read coalesced 128-byte row segments, split them into hi/lo in
+//     registers and write both with tcgen05.st into a TMEM ring; the MMA takes A from TMEM, so shared memory
+//     carries only the weight ring.  (A first version staged A in shared memory, in the MN-major
+//     SWIZZLE_128B_BASE32B layout -- the only MN-major layout tcgen05 accepts for 32-bit operands; it was
+//     bound by the 128 B/clk shared-memory port: 7 KB of operands per 48-cycle N=96 MMA.)
 //   * one elected thread issues, per 8-k step, hi.hi + lo.hi + hi.lo (fp32 accumulate in TMEM): the
 //     dropped lo.lo term is below 2^-22 relative, so results stay inside the fp32 rtol 1e-4 parity bar,
 //     which plain TF32 (10-bit mantissa) would not.
@@ -29,10 +30,11 @@
 
 namespace {
 
-constexpr int kThreads = 256;          // warp 0: TMA(B)  warp 1: MMA  warp 2: TMEM alloc  warp 3: idle  warps 4-7: A producers + epilogue
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 384;          // warp 0: TMA(B)  warps 1,3: MMA issuers  warp 2: TMEM alloc  warps 4-11: A producers + epilogue
+constexpr int kProducerThreads = 256;
 constexpr int KS = 16;                 // k per stage
 constexpr int BM = 128;                // batch columns per UMMA (M)
+constexpr int kSuperTiles = 16;        // rasterisation super-tile: 16 x 128 = 2048 batch columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,10 +51,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // suspend-time hint: sleep in hardware, do not spin
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "DONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -84,45 +86,81 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 constexpr uint32_t kLayoutSW128B32 = 1, kLayoutSW64 = 4;
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, A MN-major, B K-major
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, A (TMEM) and B K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int NB, bool RELU>
+// A operand from tensor memory: D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int NW>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const uint32_t (&r)[NW]) {
+    if constexpr (NW == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    }
+}
+
+// Shared memory holds only the weight ring; the activation operand lives in TMEM:
+//   TMEM columns [0, NB*Gp)                      fp32 accumulators, one Gp-wide block per batch tile
+//   TMEM columns [a0 + (sa*NB + b)*32, +32)      A ring: 16 hi columns then 16 lo columns (lane = batch element, column = k)
+// A tf32 UMMA with N = 96 needs 4 KB of A and 3 KB of B per 48 cycles; with A in shared memory that is 146 B/clk, above
+// the 128 B/clk shared-memory port, so the tensor pipe starves.  From TMEM the A operand costs no shared-memory
+// bandwidth and the producers' stores (tcgen05.st) bypass shared memory as well.
+template <int NB, bool RELU, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-             const int32_t *__restrict__ rows, const int32_t *__restrict__ cols,
-             int G, int Gp, int K_pad, int chunks_per_group, int n_stages, uint32_t tmem_cols,
+             const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k,
+             int G, int Gp, int K_pad, int chunks_per_group, int64_t n_items, int64_t n_tiles, int n_b, int n_a, uint32_t a0,
              const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
 {
     extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte alignment for the swizzle atoms
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int a_tile_bytes = 4 * 4 * 512;                        // [k-atom 4][batch-atom 4][512] per batch tile, hi or lo
-    const int a_stage_bytes = NB * 2 * a_tile_bytes;             // NB batch tiles x (hi, lo)
     const int b_plane_bytes = Gp * KS * 4;                       // Gp rows x 64 B
-    const int stage_bytes = a_stage_bytes + 2 * b_plane_bytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)n_stages * stage_bytes);
-    uint64_t *empty_bar = full_bar + n_stages;
-    uint64_t *accum_bar = empty_bar + n_stages;
+    const int stage_bytes = 2 * b_plane_bytes;                   // hi plane, lo plane
+    int32_t *s_cols = reinterpret_cast<int32_t *>(smem + (size_t)n_b * stage_bytes);        // the group's gather list, K_pad entries
+    uint64_t *fullB = reinterpret_cast<uint64_t *>(smem + (size_t)n_b * stage_bytes + (size_t)K_pad * 4);
+    uint64_t *emptyB = fullB + n_b;
+    uint64_t *fullA = emptyB + n_b;
+    uint64_t *emptyA = fullA + n_a;
+    uint64_t *accum_bar = emptyA + n_a;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t g = blockIdx.x / chunks_per_group;             // pattern group
-    const int gchunk = (int)(blockIdx.x - g * chunks_per_group); // 256-row chunk of a very tall group
+    const KnRaster rt = kn_raster(blockIdx.x, n_items, n_tiles, kSuperTiles / NB);
+    const int64_t g = rt.item / chunks_per_group;                // pattern group
+    const int gchunk = (int)(rt.item - g * chunks_per_group);    // 256-row chunk of a very tall group
     const int row0 = gchunk * 256;                               // first group row handled here
-    const int64_t nbase = (int64_t)blockIdx.y * (BM * NB);
-    const int n_ksteps = K_pad / KS;
+    const int64_t nbase = rt.tile * (BM * NB);
+    // groups of one class share K_pad (storage) but loop only over their own K (edge / corner pixels have fewer taps)
+    const int n_ksteps = group_k ? (__ldg(group_k + g) + KS - 1) / KS : K_pad / KS;
+    // DUAL (Gp <= 128): the hi and lo weight planes are adjacent in shared memory, so ONE UMMA with N = 2*Gp computes
+    // x_hi.[w_hi ; w_lo] into two accumulator blocks (summed in the epilogue): 2 instructions per k-step instead of 3.
+    const int acc_w = DUAL ? 2 * Gp : Gp;                        // accumulator columns per batch tile
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < n_stages; s++) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        // NB MMA issuers (one per batch tile): each commits once per stage to both rings and once to accum_bar
+        for (int s = 0; s < n_b; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NB); }
+        for (int s = 0; s < n_a; s++) { mbar_init(&fullA[s], kProducerThreads); mbar_init(&emptyA[s], NB); }
+        mbar_init(accum_bar, NB);
         fence_barrier_init();
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    // the column list is read once per CTA: a gather then never waits for an index load before it can issue
+    for (int i = tid; i < n_ksteps * KS; i += kThreads) s_cols[i] = __ldg(cols + g * (int64_t)K_pad + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -133,117 +171,148 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         if (lane == 0) {
             const int grow = (int)(g * G) + row0;
             for (int ks = 0; ks < n_ksteps; ks++) {
-                const int s = ks % n_stages;
-                const uint32_t ph = (uint32_t)(ks / n_stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                unsigned char *bs = smem + (size_t)s * stage_bytes + a_stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], 2u * (uint32_t)b_plane_bytes);
-                tma_load_2d(bs, &map_hi, ks * KS, grow, &full_bar[s]);
-                tma_load_2d(bs + b_plane_bytes, &map_lo, ks * KS, grow, &full_bar[s]);
+                const int s = ks % n_b;
+                const uint32_t ph = (uint32_t)(ks / n_b) & 1u;
+                mbar_wait(&emptyB[s], ph ^ 1u);
+                unsigned char *bs = smem + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&fullB[s], 2u * (uint32_t)b_plane_bytes);
+                tma_load_2d(bs, &map_hi, ks * KS, grow, &fullB[s]);
+                tma_load_2d(bs + b_plane_bytes, &map_lo, ks * KS, grow, &fullB[s]);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || (warp == 3 && NB == 2)) {
+        // ===== MMA issuers: one elected thread per batch tile =====
+        // A single thread issues one tcgen05.mma per ~117 cycles whatever its shape (measured, scratch/umma_rate.cu),
+        // while a tf32 128 x 96 x 8 MMA occupies the tensor pipe for only 48 cycles: one issuer per accumulator
+        // (warp 1 -> batch tile 0, warp 3 -> batch tile 1) keeps the pipe fed for N < 256.
         if (lane == 0) {
+            const int b = (warp == 1) ? 0 : 1;
             const uint32_t idesc = make_idesc(BM, Gp);
+            const uint32_t idesc2 = make_idesc(BM, 2 * Gp);
+            const uint32_t d = tmem_base + (uint32_t)(b * acc_w);
+            const uint64_t desc0 = make_desc(smem_u32(smem), 16, 512, kLayoutSW64);
             for (int ks = 0; ks < n_ksteps; ks++) {
-                const int s = ks % n_stages;
-                const uint32_t ph = (uint32_t)(ks / n_stages) & 1u;
-                mbar_wait(&full_bar[s], ph);
+                const int sb = ks % n_b, sa = ks % n_a;
+                mbar_wait(&fullB[sb], (uint32_t)(ks / n_b) & 1u);
+                mbar_wait(&fullA[sa], (uint32_t)(ks / n_a) & 1u);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + a_stage_bytes;
+                const uint32_t ta = tmem_base + a0 + (uint32_t)((sa * NB + b) * 32);
+                // B: K-major SW64 (64-byte rows), 8-row groups 512 B apart; stage / plane / k-step only move the
+                // 14-bit start-address field (units of 16 B), so the descriptor is one 64-bit add away from desc0
+                const uint64_t dstage = desc0 + (uint64_t)(((uint32_t)sb * (uint32_t)stage_bytes) >> 4);
 #pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    const uint32_t a_hi = sa + b * 2 * a_tile_bytes, a_lo = a_hi + a_tile_bytes;
-#pragma unroll
-                    for (int kk = 0; kk < KS / 8; kk++) {
-                        // A: MN-major SWIZZLE_128B_BASE32B (the only MN-major layout for 32-bit operands): atom = 32 batch x 4 k
-                        // (512 B), LBO = 512 (next 32 batch columns), SBO = 2048 (next 4 k); one MMA (8 k) spans two k-atoms
-                        const uint64_t da_hi = make_desc(a_hi + kk * 4096, 512, 2048, kLayoutSW128B32);
-                        const uint64_t da_lo = make_desc(a_lo + kk * 4096, 512, 2048, kLayoutSW128B32);
-                        // B: K-major SW64 (64-byte rows), 8-row groups 512 B apart; second k step = +32 B
-                        const uint64_t db_hi = make_desc(sb + kk * 32, 16, 512, kLayoutSW64);
-                        const uint64_t db_lo = make_desc(sb + b_plane_bytes + kk * 32, 16, 512, kLayoutSW64);
-                        const uint32_t d = tmem_base + (uint32_t)(b * Gp);
-                        umma_tf32(d, da_hi, db_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
-                        umma_tf32(d, da_lo, db_hi, idesc, 1u);
-                        umma_tf32(d, da_hi, db_lo, idesc, 1u);
+                for (int kk = 0; kk < KS / 8; kk++) {
+                    const uint64_t db_hi = dstage + (uint64_t)(kk * 2);
+                    const uint64_t db_lo = db_hi + (uint64_t)(b_plane_bytes >> 4);
+                    if (DUAL) {
+                        umma_tf32_ts(d, ta + kk * 8, db_hi, idesc2, (ks > 0 || kk > 0) ? 1u : 0u); // x_hi . [w_hi ; w_lo]
+                        umma_tf32_ts(d, ta + 16 + kk * 8, db_hi, idesc, 1u);                       // x_lo . w_hi
+                    } else {
+                        umma_tf32_ts(d, ta + kk * 8, db_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);  // x_hi . w_hi
+                        umma_tf32_ts(d, ta + 16 + kk * 8, db_hi, idesc, 1u);                       // x_lo . w_hi
+                        umma_tf32_ts(d, ta + kk * 8, db_lo, idesc, 1u);                            // x_hi . w_lo
                     }
                 }
-                umma_commit(&empty_bar[s]);                    // frees the stage when these MMAs retire
+                umma_commit(&emptyB[sb]);                      // both rings are released when every issuer's MMAs retire
+                umma_commit(&emptyA[sa]);
             }
             umma_commit(accum_bar);
         }
     } else if (warp >= 4) {
-        // ===== A producers: gather X rows, split hi/lo, store in UMMA MN-major SW128 layout =====
-        const int pt = tid - 128;                               // 0..127
-        const int chunk = pt & 31;                              // 16-byte chunk inside the 512-byte row segment
-        const int rsub = pt >> 5;                               // 0..3
-        const int32_t *__restrict__ cg = cols + g * (int64_t)K_pad;
-        const int m_atom = chunk >> 3, j = chunk & 7;
-        for (int ks = 0; ks < n_ksteps; ks++) {
-            const int s = ks % n_stages;
-            const uint32_t ph = (uint32_t)(ks / n_stages) & 1u;
-            float4 v[NB][4];
+        // ===== A producers: gather X, split hi/lo, tcgen05.st into the TMEM A ring =====
+        // thread = one batch element (TMEM lane); it loads X[cols[k]][n] for the k's of its stage share -- each warp
+        // load is one coalesced 128-byte row segment -- and runs PD stages ahead of the TMEM stores (register ring).
+        const int q = warp & 3;                                 // TMEM lane quarter of this warp
+        const int sel = (warp - 4) >> 2;                        // NB == 2: batch tile; NB == 1: k half of the stage
+        constexpr int KW = (NB == 2) ? 16 : 8;                  // k values per thread and stage
+        constexpr int PD = 4;                                   // prefetch distance in stages
+        const int b_mine = (NB == 2) ? sel : 0;
+        const int k0 = (NB == 2) ? 0 : sel * 8;
+        const int64_t n = nbase + b_mine * BM + q * 32 + lane;
+        const bool n_ok = n < n_vecs;
+        const float *__restrict__ xn = X + (n_ok ? n : 0);
+        const uint32_t ldx32 = (uint32_t)ldx;
+        float buf[PD][KW];
+
+        auto gather = [&](float (&v)[KW], int ks) {
+            const int4 *cp = reinterpret_cast<const int4 *>(s_cols + ks * KS + k0);             // 16-byte aligned
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int k = rsub + 4 * i;                     // 0..15 inside the stage
-                const int32_t c = __ldg(cg + ks * KS + k);
-                const float *__restrict__ xr = X + (int64_t)c * ldx;
+            for (int i4 = 0; i4 < KW / 4; i4++) {
+                const int4 c = cp[i4];                          // warp-broadcast LDS.128: 4 column indices
+                // one IMAD.WIDE.U32 per address (row index and leading dimension are both < 2^32)
+                v[4 * i4 + 0] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.x * ldx32) : 0.0f;
+                v[4 * i4 + 1] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.y * ldx32) : 0.0f;
+                v[4 * i4 + 2] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.z * ldx32) : 0.0f;
+                v[4 * i4 + 3] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.w * ldx32) : 0.0f;
+            }
+        };
+        auto publish = [&](const float (&v)[KW], int ks) {
+            const int sa = ks % n_a;
+            uint32_t hi[KW], lo[KW];
 #pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    const int64_t n = nbase + b * BM + chunk * 4;
-                    v[b][i] = (n < n_vecs) ? __ldg(reinterpret_cast<const float4 *>(xr + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < KW; i++) {
+                hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+                lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+            }
+            mbar_wait(&emptyA[sa], ((uint32_t)(ks / n_a) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a0 + (uint32_t)((sa * NB + b_mine) * 32 + k0);
+            tmem_store<KW>(ta, hi);
+            tmem_store<KW>(ta + 16, lo);
+        };
+        // completing a stage (wait for the TMEM stores, then signal the issuers) is deferred until the next
+        // gather has been issued, so the store latency overlaps with load issue instead of serialising every stage
+        auto finish = [&](int ks) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&fullA[ks % n_a]);
+        };
+#pragma unroll
+        for (int d = 0; d < PD; d++)
+            if (d < n_ksteps) gather(buf[d], d);
+        for (int ks0 = 0; ks0 < n_ksteps; ks0 += PD) {
+#pragma unroll
+            for (int d = 0; d < PD; d++) {
+                const int ks = ks0 + d;
+                if (ks < n_ksteps) {
+                    publish(buf[d], ks);
+                    if (ks + PD < n_ksteps) gather(buf[d], ks + PD);
+                    finish(ks);
                 }
             }
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            unsigned char *as = smem + (size_t)s * stage_bytes;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int k = rsub + 4 * i;
-                const int k4 = k & 3;
-                const int off = (k >> 2) * 2048 + m_atom * 512 + k4 * 128 + ((((j >> 1) ^ k4) << 5) | ((j & 1) << 4));
-#pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    const float4 x = v[b][i];
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
-                    *reinterpret_cast<float4 *>(as + b * 2 * a_tile_bytes + off) = hi;
-                    *reinterpret_cast<float4 *>(as + b * 2 * a_tile_bytes + a_tile_bytes + off) = lo;
-                }
-            }
-            fence_proxy_async();                                // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(&full_bar[s]);
         }
 
         // ===== epilogue: TMEM -> registers -> ReLU -> Y =====
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int q = warp - 4;                                 // TMEM lane quarter owned by this warp
+        const int half = (warp - 4) >> 2;                       // two warps per lane quarter: even / odd 16-column chunks
         const int g_valid = min(Gp, G - row0);
         const int32_t *__restrict__ rg = rows + g * (int64_t)G + row0;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
-            const int64_t n = nbase + b * BM + q * 32 + lane;
-            for (int c0 = 0; c0 < Gp; c0 += 16) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Gp + c0);
+            const int64_t ne = nbase + b * BM + q * 32 + lane;
+            for (int c0 = half * 16; c0 < Gp; c0 += 32) {
+                uint32_t r[16], r2[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * acc_w + c0);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(taddr));
+                if (DUAL) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+                                   "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+                                 : "r"(taddr + (uint32_t)Gp));
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (n < n_vecs) {
+                if (ne < n_vecs) {
 #pragma unroll
                     for (int t = 0; t < 16; t++) {
                         if (c0 + t < g_valid) {
                             float y = __uint_as_float(r[t]);
+                            if (DUAL) y += __uint_as_float(r2[t]);
                             if (RELU) y = fmaxf(y, 0.0f);
-                            Y[(int64_t)__ldg(rg + c0 + t) * ldy + n] = y;
+                            Y[(int64_t)__ldg(rg + c0 + t) * ldy + ne] = y;
                         }
                     }
                 }
@@ -255,7 +324,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(tmem_cols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base));
     }
 }
 
@@ -285,31 +354,31 @@ PFN_encodeTiled get_encode() {
     return fn;
 }
 
-template <int NB>
-int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, int64_t n_groups, int G, int K_pad,
+template <int NB, bool DUAL>
+int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
     const int chunks_per_group = (G + 255) / 256;
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
-    const int a_stage = NB * 2 * 8192, b_plane = Gp * KS * 4, stage = a_stage + 2 * b_plane;
-    int n_stages = (int)((227 * 1024 - 1024 - 256) / stage);
-    if (n_stages > 6) n_stages = 6;
-    KN_REQUIRE(n_stages >= 2, "spmm_pg_tc: stage does not fit shared memory");
-    const size_t smem = (size_t)n_stages * stage + 1024 + 256;
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < NB * Gp) tmem_cols <<= 1;
-    KN_REQUIRE(tmem_cols <= 512, "spmm_pg_tc: accumulator does not fit TMEM");
+    const int stage = 2 * Gp * KS * 4;
+    int n_b = (int)((220 * 1024 - (int64_t)K_pad * 4) / stage);   // weight ring in shared memory, next to the column list
+    if (n_b > 8) n_b = 8;
+    const uint32_t a0 = (uint32_t)(NB * (DUAL ? 2 * Gp : Gp));   // activation ring in TMEM, after the accumulators
+    int n_a = (int)((512 - a0) / (NB * 32));
+    if (n_a > 6) n_a = 6;
+    KN_REQUIRE(n_b >= 2 && n_a >= 2, "spmm_pg_tc: rings do not fit (Gp=%d NB=%d)", Gp, NB);
+    const size_t smem = (size_t)n_b * stage + (size_t)K_pad * 4 + 1024 + 512;
     const int64_t gx = n_groups * chunks_per_group, gy = kn_cdiv(n_vecs, BM * NB);
-    KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm_pg_tc: grid too large");
+    KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg_tc: grid too large");
     static bool configured = false;
     if (!configured) {
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    if (relu) pg_tc_kernel<NB, true><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, G, Gp, K_pad, chunks_per_group, n_stages, tmem_cols, X, ldx, Y, ldy, n_vecs);
-    else      pg_tc_kernel<NB, false><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, G, Gp, K_pad, chunks_per_group, n_stages, tmem_cols, X, ldx, Y, ldy, n_vecs);
+    dim3 grid((unsigned)(gx * gy));
+    if (relu) pg_tc_kernel<NB, true, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
+    else      pg_tc_kernel<NB, false, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -346,19 +415,24 @@ KN_API int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64
     return KN_OK;
 }
 
-KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, int64_t n_groups, int32_t G, int32_t K_pad,
+KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
                              const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KS == 0, "spmm_pg_tc: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg_tc: bad leading dimension");
     if (n_groups == 0 || n_vecs == 0) return KN_OK;
     KN_REQUIRE(maps_host && rows && cols && X && Y, "spmm_pg_tc: null pointer");
     KN_REQUIRE(n_vecs % 4 == 0 && ldx % 4 == 0 && (((uintptr_t)X) & 15) == 0, "spmm_pg_tc: n_vecs and ldx must be multiples of 4, X 16-byte aligned");
+    KN_REQUIRE(ldx < 0xffffffffLL, "spmm_pg_tc: leading dimension must fit 32 bits");
     CUtensorMap maps[2];
     memcpy(maps, maps_host, 2 * sizeof(CUtensorMap));
     const bool relu = (flags & KN_SPMM_RELU) != 0;
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
-    // two batch tiles per CTA share every weight stage when the accumulators fit TMEM and the batch is wide enough
-    if (2 * Gp <= 512 && n_vecs > BM)
-        return launch_tc<2>(maps, rows, cols, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
-    return launch_tc<1>(maps, rows, cols, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    // two batch tiles per CTA share every weight stage when accumulators + a >= 2-deep activation ring fit TMEM
+    if (Gp <= 96 && n_vecs > BM)          // 2 tiles x 2*Gp accumulator columns + a 2-deep activation ring fit the 512 TMEM columns
+        return launch_tc<2, true>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    if (Gp <= 128)
+        return launch_tc<1, true>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    if (2 * Gp + 2 * 64 <= 512 && n_vecs > BM)
+        return launch_tc<2, false>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    return launch_tc<1, false>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
 }

@@ -77,7 +77,7 @@ class KeyedLayer(nn.Module):
             raise ValueError('unsupported layer type "%s"' % str(type(module)))
 
         if tileshape is None:
-            self.W.optimize()          # pattern-grouped execution format for batched forward (csrc/pgroup.cu)
+            self.W.optimize()          # pattern-grouped execution format for batched forward (no-op if the builder made it)
         if tileshape is not None:
             from .tiled import tile_keyed_layer
             self.W = tile_keyed_layer(self.W, module, inshape, outshape, tileshape)

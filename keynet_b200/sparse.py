@@ -407,6 +407,8 @@ class PatternGroups(object):
 
     TC_MIN_G = 32          # groups at least this tall are "true small GEMMs": tcgen05 path
     TC_MIN_BATCH = 128
+    TC_MAX_K = 32768       # the group's column list is staged in shared memory next to the weight ring
+    TC_MIN_K = 128         # shorter reductions do not amortise the per-CTA TMEM / barrier set-up: fp32 FMA kernel
 
     def __init__(self):
         self.classes = []
@@ -417,6 +419,7 @@ class PatternGroups(object):
 
     @staticmethod
     def build(W, min_group=4, max_pad_waste=0.25):
+        """max_pad_waste: a class is split when a group's K falls below this fraction of the class maximum."""
         L = _native.lib()
         dev = W._data.device
         (R, C) = W.shape
@@ -448,14 +451,15 @@ class PatternGroups(object):
         in_group = torch.zeros(R, dtype=torch.bool, device=dev)
         for G in torch.unique(gsize[sel]).tolist():
             gi = torch.nonzero(sel & (gsize == G)).reshape(-1)
-            # split the class where padding every group to the widest one would waste too much
+            # one class per group height: groups share K_pad (storage) and carry their own K, so border pixels with
+            # fewer taps cost neither extra launches nor padded arithmetic.  Only a very ragged class is split.
             Ks = K[gi]
             (Ks_sorted, o) = torch.sort(Ks, descending=True)
             gi = gi[o]
             bounds = [0]
             Kl = Ks_sorted.tolist()
             for (j, k) in enumerate(Kl):
-                if k < (1.0 - max_pad_waste) * Kl[bounds[-1]]:
+                if k < max_pad_waste * Kl[bounds[-1]]:
                     bounds.append(j)
             bounds.append(len(Kl))
             for (b0, b1) in zip(bounds[:-1], bounds[1:]):
@@ -470,8 +474,9 @@ class PatternGroups(object):
                 cols = torch.empty(ng * K_pad, dtype=torch.int32, device=dev)
                 vals = torch.empty(ng * G * K_pad, dtype=torch.float32, device=dev)
                 check(L.kn_pg_pack(ptr(indptr), ptr(indices), ptr(data), ptr(rows64), ng, int(G), K_pad, ptr(cols), ptr(vals), stream_ptr()))
-                cls = dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals, tc=None)
-                if int(G) >= PatternGroups.TC_MIN_G and tensor_cores_enabled():
+                cls = dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals, tc=None,
+                           group_k=K[g_sub].to(torch.int32).contiguous())
+                if int(G) >= PatternGroups.TC_MIN_G and PatternGroups.TC_MIN_K <= K_pad <= PatternGroups.TC_MAX_K and tensor_cores_enabled():
                     # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
                     (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
                     check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
@@ -501,10 +506,10 @@ class PatternGroups(object):
         flags = _native.KN_SPMM_RELU if relu else 0
         for c in self.classes:
             if c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
-                check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), c['n_groups'], c['G'], c['K_pad'],
+                check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), c['n_groups'], c['G'], c['K_pad'],
                                           ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
             else:
-                check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), c['n_groups'], c['G'], c['K_pad'],
+                check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), ptr(c['group_k']), c['n_groups'], c['G'], c['K_pad'],
                                        ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
         r = self.rest
         if r is not None:
@@ -555,7 +560,7 @@ def _emitted_taps(U, k, stride):
     return np.array([np.any((u + p >= 0) & (u + p < U)) for p in range(-h, h + 1)])
 
 
-def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None):
+def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None, keep_zeros=False):
     """Apply column map/scales of Ainv and row scales of A to an already row-gathered CSR."""
     (indptr, indices, data) = csr
     L = _native.lib()
@@ -572,8 +577,8 @@ def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None):
             col_scale = torch.from_numpy(Ainv.scale).to(dev)
     return _two_phase(
         n_rows,
-        lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), ptr(row_nnz), stream_ptr())),
-        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols, ptr(col_map), ptr(row_scale), ptr(col_scale),
+        lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), int(keep_zeros), ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols, ptr(col_map), ptr(row_scale), ptr(col_scale), int(keep_zeros),
                                                       ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
         dev)
 
@@ -618,7 +623,7 @@ def _conv_weights_rounded(inshape, f, bias, stride):
     return (fq, bq, (C, U, V, M, P, Q))
 
 
-def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None):
+def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True):
     """W_hat = A . toeplitz(conv2d) . Ainv built on the GPU for monomial keys (keynet/layer.py:32-35).
 
     rows=(r0, r1) builds only that row range of W_hat (row shard); indptr then has r1-r0+1 entries."""
@@ -628,9 +633,15 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None):
     K = C * U * V + 1
     desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1)
     (ids, r0, r1) = _row_ids(A, R, rows, dev)
-    csr = _toeplitz_rows(desc, fq, bq, ids, r1 - r0, dev)
-    csr = _keycompile(csr, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
-    return SparseMatrix(((r1 - r0, K), *csr), device=dev)
+    csr0 = _toeplitz_rows(desc, fq, bq, ids, r1 - r0, dev)
+    csr = _keycompile(csr0, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
+    W = SparseMatrix(((r1 - r0, K), *csr), device=dev)
+    if build_groups and W.nnz() >= 4096:
+        # pattern groups come from the STRUCTURAL matrix (exact zeros kept): every output pixel keeps its full
+        # M-row group even where the reference's offset rounding turned a tiny weight into a dropped zero
+        S = SparseMatrix(((r1 - r0, K), *_keycompile(csr0, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1), keep_zeros=True)), device=dev)
+        W._pg = PatternGroups.build(S)
+    return W
 
 
 def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None):

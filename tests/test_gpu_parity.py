@@ -438,6 +438,7 @@ def test_pattern_groups_tensor_core_path(M, C, N):
     (U, V) = (6, 8)
     perm_gain = lambda n: sparse.MonomialKey(np.concatenate([rs.permutation(n - 1), [n - 1]]), np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32))
     sparse.tensor_cores_enabled(True)
+    sparse.PatternGroups.TC_MIN_K = 32                # exercise the tensor-core kernel also on these short reductions
     W = sparse.keyed_toeplitz_conv2d((C, U, V), rs.randn(M, C, 3, 3).astype(np.float32), rs.randn(M).astype(np.float32), 1,
                                      perm_gain(M * U * V + 1), perm_gain(C * U * V + 1).transpose())
     W._pg = sparse.PatternGroups.build(W, min_group=4)
@@ -459,4 +460,5 @@ def test_pattern_groups_tensor_core_path(M, C, N):
     assert _close(y_tc, ref), (np.abs(y_tc - ref).max(), np.abs(ref).max())
     # no ReLU variant
     y2 = sparse.spmm(W, Xd, relu=False).cpu().numpy()
+    sparse.PatternGroups.TC_MIN_K = 128
     assert _close(y2, ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=False, threads=8))
