@@ -68,6 +68,30 @@ def hbm_peak():
     return (HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md)')
 
 
+def tensor_peak():
+    """Dense bf16 tensor throughput measured on this pool's B200s (sustained figure: the kernel is timed inside a long step)."""
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return (float(json.load(f)['bf16_tflops_sustained']), 'measured bf16 sustained (MEASURED_PEAKS.json)')
+        except Exception:
+            pass
+    return (1400.0, 'fallback (B200_PROFILING.md, sustained)')
+
+
+def profiled_traffic(net, batch, layer):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/traffic.json); None if no capture matches this workload."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        return t.get('%s:%d:%s' % (net, batch, layer))
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
@@ -296,19 +320,38 @@ def main():
 
     if rank == 0:
         (peak, peak_src) = hbm_peak()
+        (tpeak, tpeak_src) = tensor_peak()
         # per-layer launch durations measured inside the timed region (CUDA events on the launch stream)
         per_layer = plan.layer_times_ms_mean(K)
         alg = dict(plan.algorithmic_bytes())
+        flops = {name: 2.0 * W.nnz() * N for (name, W, _) in plan.layers}
         (dom, dom_ms) = max(per_layer, key=lambda kv: kv[1])
-        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-        total_alg = sum(alg.values())
         domW = [W for (name, W, _) in plan.layers if name == dom][0]
-        kname = ('pg_simt_kernel (pattern groups %s)' % str(domW._pg.summary()['classes'])) if (domW._pg is not None and N >= 32 and N % 4 == 0) else 'spmm_rowwarp_kernel'
-        roofline = {'bound': 'hbm', 'kernel': '%s on layer %s' % (kname, dom), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'peak_source': peak_src, 'launch_ms': dom_ms, 'algorithmic_bytes_per_launch': alg[dom],
-                    'share_of_step': dom_ms / (ms / K),
-                    'network': {'algorithmic_bytes_per_step': total_alg, 'achieved': total_alg / (ms / K * 1e-3) / 1e9, 'frac': total_alg / (ms / K * 1e-3) / 1e9 / peak},
-                    'layers_ms': {k: round(v, 4) for (k, v) in per_layer}}
+        grouped = domW._pg is not None and N >= 32 and N % 4 == 0
+        on_tc = grouped and any(c['tc'] is not None for c in domW._pg.classes) and N >= 128
+        kname = ('pg_tc_kernel (tcgen05 3xTF32)' if on_tc else 'pg_simt_kernel / pg_small_kernel (fp32 FMA)') if grouped else 'spmm_rowwarp_kernel'
+        if grouped:
+            kname += ', pattern groups (G, K_pad, n_groups)=%s' % str(domW._pg.summary()['classes'])
+        hbm_achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+        total_alg = sum(alg.values())
+        traffic = profiled_traffic(args.net, N, dom)
+        if on_tc:
+            # this launch is bound by the tensor pipe, not HBM: arithmetic intensity 2*nnz*N / bytes is far above the
+            # machine balance at batch 4096.  achieved = ALGORITHMIC flops (2*nnz*N) / launch time; peak = measured dense
+            # bf16 (the only measured tensor number).  kind::tf32 runs at half the bf16 rate and the 3xTF32 split issues
+            # 3 MMAs per product, so the ceiling for this arithmetic is peak/6.
+            achieved = flops[dom] / (dom_ms * 1e-3) / 1e12
+            roofline = {'bound': 'tensor', 'kernel': '%s on layer %s' % (kname, dom), 'achieved': achieved, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': achieved / tpeak,
+                        'traffic': traffic, 'peak_source': tpeak_src, 'ceiling_3xtf32': tpeak / 6.0, 'frac_of_3xtf32_ceiling': achieved / (tpeak / 6.0),
+                        'hbm': {'achieved': hbm_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': hbm_achieved / peak, 'peak_source': peak_src}}
+        else:
+            roofline = {'bound': 'hbm', 'kernel': '%s on layer %s' % (kname, dom), 'achieved': hbm_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': hbm_achieved / peak,
+                        'traffic': traffic, 'peak_source': peak_src}
+        roofline.update({'launch_ms': dom_ms, 'algorithmic_bytes_per_launch': alg[dom], 'algorithmic_flops_per_launch': flops[dom],
+                         'share_of_step': dom_ms / (ms / K),
+                         'network': {'algorithmic_bytes_per_step': total_alg, 'hbm_achieved_gbs': total_alg / (ms / K * 1e-3) / 1e9, 'hbm_frac': total_alg / (ms / K * 1e-3) / 1e9 / peak,
+                                     'algorithmic_tflops': sum(flops.values()) / (ms / K * 1e-3) / 1e12},
+                         'layers_ms': {k: round(v, 4) for (k, v) in per_layer}})
         out = {'metric': 'encrypted_images_per_sec', 'value': world * N * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': args.warmup,
                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': wl['label'], 'batch_per_gpu': N, 'global_batch': N * world, 'parallelism': 'dp%d replicas, no collective' % world,

@@ -196,6 +196,87 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
     }
 }
 
+// ---- small groups (G <= 16, K <= 128; LeNet-sized layers): one warp per (group, batch super-tile) -------------
+// The warp stages its group's column list and value block (transposed to [k][row]) in shared memory once, then
+// walks the 128-column batch tiles of its super-tile: per k one coalesced LDG.128 of the gathered X row segment
+// feeds 4*G FFMA (values come as warp-broadcast LDS.128), exact K (no padding), G rows x 512 B written per tile.
+template <int GM, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
+                const int32_t *__restrict__ group_k, int64_t n_groups, int G, int K_pad, int64_t n_supers, int tiles_per_super,
+                const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = K_pad * (GM + 1);                                   // floats: vals [K_pad][GM] + cols [K_pad]
+    float *s_val = reinterpret_cast<float *>(smem_raw) + (size_t)warp * per_warp;
+    int32_t *s_col = reinterpret_cast<int32_t *>(s_val + (size_t)K_pad * GM);
+    const int64_t item = (int64_t)blockIdx.x * (kThreads / 32) + warp;       // groups fastest inside a super-tile
+    if (item >= n_groups * n_supers) return;
+    const int64_t sup = item / n_groups, g = item - sup * n_groups;
+    const int K = group_k ? __ldg(group_k + g) : K_pad;
+
+    for (int i = lane; i < K; i += 32) s_col[i] = __ldg(cols + g * (int64_t)K_pad + i);
+    for (int i = lane; i < K * GM; i += 32) {
+        const int k = i / GM, r = i - k * GM;
+        s_val[i] = (r < G) ? __ldg(vals + (g * G + r) * (int64_t)K_pad + k) : 0.0f;
+    }
+    __syncwarp();
+
+    for (int t = 0; t < tiles_per_super; t++) {
+        const int64_t n0 = (sup * tiles_per_super + t) * TN + lane * 4;
+        if (n0 - lane * 4 >= n_vecs) break;                                  // warp-uniform
+        const bool ok = n0 < n_vecs;
+        const float *__restrict__ xb = X + (ok ? n0 : 0);
+        float acc[GM][4];
+#pragma unroll
+        for (int r = 0; r < GM; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f; }
+#pragma unroll 2
+        for (int k = 0; k < K; k++) {
+            const float4 x = ok ? __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)s_col[k] * ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r4 = 0; r4 < GM; r4 += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(&s_val[k * GM + r4]);
+                acc[r4 + 0][0] = fmaf(a.x, x.x, acc[r4 + 0][0]); acc[r4 + 0][1] = fmaf(a.x, x.y, acc[r4 + 0][1]); acc[r4 + 0][2] = fmaf(a.x, x.z, acc[r4 + 0][2]); acc[r4 + 0][3] = fmaf(a.x, x.w, acc[r4 + 0][3]);
+                acc[r4 + 1][0] = fmaf(a.y, x.x, acc[r4 + 1][0]); acc[r4 + 1][1] = fmaf(a.y, x.y, acc[r4 + 1][1]); acc[r4 + 1][2] = fmaf(a.y, x.z, acc[r4 + 1][2]); acc[r4 + 1][3] = fmaf(a.y, x.w, acc[r4 + 1][3]);
+                acc[r4 + 2][0] = fmaf(a.z, x.x, acc[r4 + 2][0]); acc[r4 + 2][1] = fmaf(a.z, x.y, acc[r4 + 2][1]); acc[r4 + 2][2] = fmaf(a.z, x.z, acc[r4 + 2][2]); acc[r4 + 2][3] = fmaf(a.z, x.w, acc[r4 + 2][3]);
+                acc[r4 + 3][0] = fmaf(a.w, x.x, acc[r4 + 3][0]); acc[r4 + 3][1] = fmaf(a.w, x.y, acc[r4 + 3][1]); acc[r4 + 3][2] = fmaf(a.w, x.z, acc[r4 + 3][2]); acc[r4 + 3][3] = fmaf(a.w, x.w, acc[r4 + 3][3]);
+            }
+        }
+        if (ok) {
+#pragma unroll
+            for (int r = 0; r < GM; r++) {
+                if (r < G) {
+                    float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                    *reinterpret_cast<float4 *>(Y + (int64_t)__ldg(rows + g * G + r) * ldy + n0) = o;
+                }
+            }
+        }
+    }
+}
+
+template <int GM>
+int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
+                 const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
+{
+    const int tiles_per_super = 16;                                          // 2048 batch columns per warp work item
+    const int64_t n_tiles = kn_cdiv(n_vecs, TN), n_supers = kn_cdiv(n_tiles, tiles_per_super);
+    const int64_t n_items = n_groups * n_supers, gx = kn_cdiv(n_items, kThreads / 32);
+    KN_REQUIRE(gx <= 0x7fffffffLL, "spmm_pg(small): grid too large");
+    const size_t smem = (size_t)(kThreads / 32) * K_pad * (GM + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        KN_CUDA(cudaFuncSetAttribute(pg_small_kernel<GM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_small_kernel<GM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    if (relu) pg_small_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
+    else      pg_small_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
 template <int RW>
 int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
@@ -264,6 +345,8 @@ KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float 
                "spmm_pg: n_vecs, ldx, ldy must be multiples of 4 and X, Y 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const bool relu = (flags & KN_SPMM_RELU) != 0;
+    if (G <= 8 && K_pad <= 128)  return launch_small<8>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 16 && K_pad <= 128) return launch_small<16>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     if (G <= 8)  return launch_pg<1>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     if (G <= 16) return launch_pg<2>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     if (G <= 32) return launch_pg<4>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);

@@ -1,0 +1,122 @@
+"""Multi-GPU execution of the keyed path on one 8xB200 box, one process per GPU.
+
+  * small networks (LeNet, AllConvNet): data-parallel REPLICAS -- every rank keys the same network (same seed, same
+    keys) and runs its own slice of the batch; no collective on the data path (bench.py --gpus N).
+  * VGG16-scale keyed layers (15 G non-zeros): ROW-SHARDED.  Every rank compiles and holds only its rows of every
+    W_hat; a layer is  Y_local = W_hat[rows_r, :] . X_full  followed by one all-gather of the feature-major
+    activations over NVLink (torch.distributed / NCCL all_gather_into_tensor), ReLU fused before the gather.
+
+Sharding is expressed as ONE MORE KEY.  Rows of a conv layer are re-ordered pixel-major before they are cut into
+`world` equal chunks, so every rank owns WHOLE pattern groups (all M output channels of its pixels -- the unit the
+tensor-core kernel works on); the gathered activation buffer is therefore in shard-major order, and that order is
+folded into the next layer's column map at compile time (an integer composition with the input key).  Nothing is
+permuted at run time, and the homogeneous coordinate is kept as a local row of ones on every rank.
+
+The planner (`plan_rows`, `LayerShard`) is pure numpy so it is covered by world_size-2 gloo tests on CPU.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+
+def plan_rows(module, outshape, world):
+    """Shard-major order of the canonical output rows of one layer (homogeneous row excluded).
+
+    Returns (order, chunk): `order` = canonical row indices, pixel-major for convolutions so that chunk boundaries
+    fall between pattern groups; rank r owns order[r*chunk:(r+1)*chunk] (the last ranks may own fewer / no rows)."""
+    (C, H, W) = [int(s) for s in outshape]
+    R = C * H * W
+    if isinstance(module, nn.Conv2d) and H * W > 1:
+        order = np.arange(R, dtype=np.int64).reshape(C, H * W).T.reshape(-1)      # (pixel, channel) <- (channel, pixel)
+        px_chunk = -(-(H * W) // world)
+        chunk = px_chunk * C
+    else:
+        order = np.arange(R, dtype=np.int64)
+        chunk = -(-R // world)
+    return (order, int(chunk))
+
+
+class LayerShard(object):
+    """Bookkeeping of one row-sharded layer: which canonical rows this rank computes and where every canonical row
+    lives in the gathered buffer [world*chunk + 1] (last position = homogeneous coordinate)."""
+
+    def __init__(self, module, outshape, rank, world):
+        (order, chunk) = plan_rows(module, outshape, world)
+        R = len(order)
+        self.chunk = chunk
+        self.n_phys = world * chunk + 1
+        self.my_rows = order[rank * chunk:min(R, (rank + 1) * chunk)]
+        pos = np.empty(R + 1, dtype=np.int64)
+        pos[order] = np.arange(R)            # canonical row -> gathered position (rank-major, then order within the chunk)
+        pos[R] = world * chunk               # homogeneous coordinate
+        self.position = pos
+        self.n_rows = R + 1
+
+
+class ShardedLayerGen(object):
+    """f_module_to_keyedmodule callback for system.KeyedModel: compiles, for every keyed layer, only this rank's rows
+    with the previous layer's gathered layout folded into the column map."""
+
+    def __init__(self, rank, world, inshape):
+        (self.rank, self.world) = (int(rank), int(world))
+        self.prev_position = None            # first layer reads the sensor output in canonical order
+        self.prev_n_phys = int(np.prod(inshape)) + 1
+        self.layers = []
+
+    def __call__(self, module, inshape, outshape, A, Ainv):
+        from . import layer as _layer
+        shard = LayerShard(module, outshape, self.rank, self.world)
+        L = _layer.KeyedLayer(module, inshape, outshape, A, Ainv, rows=shard.my_rows,
+                              col_remap=self.prev_position, n_cols_phys=self.prev_n_phys)
+        L._shard = shard
+        (self.prev_position, self.prev_n_phys) = (shard.position, shard.n_phys)
+        self.layers.append(L)
+        return L
+
+
+class ShardedKeyedModel(object):
+    """Row-sharded keyed network: same constructor contract as system.Keynet(...)[1] plus (rank, world, group)."""
+
+    def __init__(self, inshape, net, rank, world, group=None, **keynet_kwargs):
+        from . import system
+        self.rank, self.world, self.group = int(rank), int(world), group
+        f_keypair = system.keypair_policy(**keynet_kwargs)
+        self.sensor = system.KeyedSensor(inshape, f_keypair('input', inshape))
+        self._gen = ShardedLayerGen(rank, world, inshape)
+        self._model = system.KeyedModel(net, inshape, self.sensor.key(), f_keypair, self._gen)
+        self._outshape = self._model._outshape
+        self.layers = self._gen.layers
+
+    def num_parameters_local(self):
+        return sum(L.nnz() for L in self.layers)
+
+    def forward_linear(self, x_cipher):
+        """x_cipher: N x (D+1) encrypted batch, identical on every rank.  Returns N x (K+1) on every rank."""
+        import torch.distributed as dist
+        from .sparse import spmm
+        dev = torch.device('cuda', torch.cuda.current_device())
+        X = x_cipher.to(dev).t().contiguous()                         # feature-major [D+1, N]
+        N = X.shape[1]
+        for L in self.layers:
+            sh = L._shard
+            relu = L._fused_relu or ('ReLU' in L._layertype)
+            Yfull = torch.empty((sh.n_phys, N), dtype=torch.float32, device=dev)
+            Yloc = Yfull[self.rank * sh.chunk:(self.rank + 1) * sh.chunk]       # this rank's slot of the gathered buffer
+            n_mine = len(sh.my_rows)
+            if n_mine < sh.chunk:
+                Yloc[n_mine:].zero_()
+            if n_mine > 0:
+                spmm(L.W, X, relu=relu, out=Yloc[:n_mine])
+            if self.world > 1:
+                dist.all_gather_into_tensor(Yfull[:self.world * sh.chunk], Yloc, group=self.group)
+            Yfull[-1].fill_(1.0)                                      # homogeneous coordinate: local, never communicated
+            X = Yfull
+        # last layer: undo the shard-major order (a gather of K+1 rows)
+        pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
+        return X[pos].t().contiguous()
+
+    def forward(self, x_cipher):
+        from . import torch as ktorch
+        y = self.forward_linear(x_cipher)
+        N = y.shape[0]
+        return ktorch.linear_to_affine(y, self._outshape if N == 1 else (N,) + tuple(self._outshape))

@@ -24,9 +24,10 @@ class FusedReLU(nn.Module):
 
 
 class KeyedLayer(nn.Module):
-    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None):
+    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None, col_remap=None, n_cols_phys=None):
         """module: nn.Conv2d | nn.AvgPool2d | nn.Linear | nn.ReLU; A / Ainv: MonomialKey (A may be None for the
-        last layer); rows=(r0, r1): build and hold only that row range of W_hat (row shard)."""
+        last layer); rows=(r0, r1) or an index array: build and hold only those rows of W_hat (row shard);
+        col_remap / n_cols_phys: physical position of every canonical input column (gathered layout, dist.py)."""
         super(KeyedLayer, self).__init__()
         self._layertype = str(type(module))
         self._inshape = inshape
@@ -46,11 +47,12 @@ class KeyedLayer(nn.Module):
             stride = module.stride[0]
             self._repr = 'Conv2d: in_channels=%d, out_channels=%d, kernel_size=%s, stride=%s' % (module.in_channels, module.out_channels, str(module.kernel_size), str(stride))
             bias = module.bias.detach().cpu().numpy() if module.bias is not None else np.zeros(module.out_channels, dtype=np.float32)
-            self.W = sparse.keyed_toeplitz_conv2d(inshape, module.weight.detach().cpu().numpy(), bias, stride, A, Ainv, rows=rows)
+            self.W = sparse.keyed_toeplitz_conv2d(inshape, module.weight.detach().cpu().numpy(), bias, stride, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys)
 
         elif isinstance(module, nn.ReLU):
             # explicit keyed ReLU (only after a batchnorm merge, keynet/system.py:97-99): W = A . Ainv, then ReLU
             self._repr = 'ReLU'
+            assert col_remap is None and (rows is None or isinstance(rows, tuple)), 'explicit keyed ReLU layers are not row-sharded by groups'
             self.W = SparseMatrix(A.dot(Ainv))
             if rows is not None:
                 self.W = self.W.row_slice(*rows)
@@ -63,11 +65,11 @@ class KeyedLayer(nn.Module):
             kernel_size = module.kernel_size if isinstance(module.kernel_size, int) else module.kernel_size[0]
             self._repr = 'AvgPool2d: kernel_size=%s, stride=%s' % (str(kernel_size), str(stride))
             # as in the reference, padding / ceil_mode of the module are ignored: centred k x k windows, divisor k*k
-            self.W = sparse.keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=rows)
+            self.W = sparse.keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys)
 
         elif isinstance(module, nn.Linear):
             self._repr = 'Linear: in_features=%d, out_features=%d' % (module.in_features, module.out_features)
-            self.W = sparse.keyed_linear(module.weight.detach(), module.bias.detach() if module.bias is not None else None, A, Ainv, rows=rows)
+            self.W = sparse.keyed_linear(module.weight.detach(), module.bias.detach() if module.bias is not None else None, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys)
 
         elif isinstance(module, nn.BatchNorm2d):
             raise ValueError('batchnorm layer should be named "mylayer_bn" for batchnorm of "mylayer" and should come right before "mylayer" to merge keyed layers')

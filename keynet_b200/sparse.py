@@ -569,29 +569,54 @@ def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None, keep_ze
         rs = A.scale if row_scale_slice is None else A.scale[row_scale_slice]
         row_scale = torch.from_numpy(np.ascontiguousarray(rs)).to(dev)
     (col_map, col_scale) = (None, None)
+    n_cols_out = n_cols if Ainv is None else int(Ainv.shape[1])      # physical column space of the compiled matrix
     if Ainv is not None:
         assert Ainv.shape[0] == n_cols
-        if not Ainv.is_unpermuted():
+        if Ainv.shape[0] != Ainv.shape[1] or not Ainv.is_unpermuted():
             col_map = torch.from_numpy(Ainv.perm.astype(np.int32)).to(dev)
         if not Ainv.is_unscaled():
             col_scale = torch.from_numpy(Ainv.scale).to(dev)
     return _two_phase(
         n_rows,
         lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), int(keep_zeros), ptr(row_nnz), stream_ptr())),
-        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols, ptr(col_map), ptr(row_scale), ptr(col_scale), int(keep_zeros),
+        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols_out, ptr(col_map), ptr(row_scale), ptr(col_scale), int(keep_zeros),
                                                       ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
         dev)
 
 
 def _row_ids(A, n_total_rows, rows, dev):
-    """Source row of every output row: A.perm restricted to the row shard `rows` = (r0, r1)."""
+    """Source row of every output row.  rows = None (all), (r0, r1) (a contiguous shard of W_hat's rows) or an int64
+    array of W_hat row indices in the order the shard stores them (row-sharding by whole pattern groups, dist.py).
+    Returns (device row ids | None, selection) where selection indexes A.scale (slice or array)."""
+    if rows is not None and not isinstance(rows, tuple):
+        sel = np.ascontiguousarray(rows, dtype=np.int64)
+        assert sel.ndim == 1 and (len(sel) == 0 or (sel.min() >= 0 and sel.max() < n_total_rows))
+        src = sel if (A is None) else A.perm[sel]
+        return (torch.from_numpy(np.ascontiguousarray(src)).to(dev), sel)
     (r0, r1) = (0, n_total_rows) if rows is None else (int(rows[0]), int(rows[1]))
     assert 0 <= r0 <= r1 <= n_total_rows
     if A is None or A.is_unpermuted():
         ids = None if (r0 == 0 and r1 == n_total_rows) else torch.arange(r0, r1, dtype=torch.int64, device=dev)
     else:
         ids = torch.from_numpy(np.ascontiguousarray(A.perm[r0:r1])).to(dev)
-    return (ids, r0, r1)
+    return (ids, slice(r0, r1))
+
+
+def _n_selected(sel, n_total):
+    return len(sel) if not isinstance(sel, slice) else (sel.stop - sel.start)
+
+
+def _remapped(Ainv, col_remap, n_cols_phys):
+    """Fold a physical column layout into the input key: column c of the canonical matrix lives at position
+    col_remap[c] of an activation buffer with n_cols_phys rows (the all-gathered, shard-major layout of dist.py)."""
+    if col_remap is None:
+        return (Ainv, Ainv.shape[0])
+    col_remap = np.ascontiguousarray(col_remap, dtype=np.int64)
+    assert len(col_remap) == Ainv.shape[0] and n_cols_phys > int(col_remap.max())
+    K = MonomialKey(Ainv.perm, Ainv.scale)
+    K.perm = col_remap[Ainv.perm]            # no longer square: only used as (col_map, col_scale) by _keycompile
+    K.shape = (Ainv.shape[0], int(n_cols_phys))
+    return (K, int(n_cols_phys))
 
 
 def _toeplitz_rows(desc, weight, bias, ids, n_rows, dev):
@@ -623,7 +648,7 @@ def _conv_weights_rounded(inshape, f, bias, stride):
     return (fq, bq, (C, U, V, M, P, Q))
 
 
-def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True):
+def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True, col_remap=None, n_cols_phys=None):
     """W_hat = A . toeplitz(conv2d) . Ainv built on the GPU for monomial keys (keynet/layer.py:32-35).
 
     rows=(r0, r1) builds only that row range of W_hat (row shard); indptr then has r1-r0+1 entries."""
@@ -632,19 +657,21 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_gr
     R = M * (U // stride) * (V // stride) + 1
     K = C * U * V + 1
     desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1)
-    (ids, r0, r1) = _row_ids(A, R, rows, dev)
-    csr0 = _toeplitz_rows(desc, fq, bq, ids, r1 - r0, dev)
-    csr = _keycompile(csr0, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
-    W = SparseMatrix(((r1 - r0, K), *csr), device=dev)
+    (ids, sel) = _row_ids(A, R, rows, dev)
+    n = _n_selected(sel, R)
+    (Ainv, Kp) = _remapped(Ainv, col_remap, n_cols_phys)
+    csr0 = _toeplitz_rows(desc, fq, bq, ids, n, dev)
+    csr = _keycompile(csr0, n, K, A, Ainv, dev, row_scale_slice=sel)
+    W = SparseMatrix(((n, Kp), *csr), device=dev)
     if build_groups and W.nnz() >= 4096:
         # pattern groups come from the STRUCTURAL matrix (exact zeros kept): every output pixel keeps its full
         # M-row group even where the reference's offset rounding turned a tiny weight into a dropped zero
-        S = SparseMatrix(((r1 - r0, K), *_keycompile(csr0, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1), keep_zeros=True)), device=dev)
+        S = SparseMatrix(((n, Kp), *_keycompile(csr0, n, K, A, Ainv, dev, row_scale_slice=sel, keep_zeros=True)), device=dev)
         W._pg = PatternGroups.build(S)
     return W
 
 
-def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None):
+def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
     """W_hat = A . toeplitz(avgpool) . Ainv (keynet/layer.py:56-59).  The reference builds C*C channel
     pairs and lets the SpGEMM drop the zero ones; here only the channel diagonal is generated."""
     dev = _device()
@@ -658,28 +685,31 @@ def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None):
     R = C * (U // stride) * (V // stride) + 1
     K = C * U * V + 1
     desc = kn_conv2d_desc(C, U, V, C, k, k, int(stride), 1, 0)     # zero bias column is dropped by the compile
-    (ids, r0, r1) = _row_ids(A, R, rows, dev)
-    csr = _toeplitz_rows(desc, wq, None, ids, r1 - r0, dev)
-    csr = _keycompile(csr, r1 - r0, K, A, Ainv, dev, row_scale_slice=slice(r0, r1))
-    return SparseMatrix(((r1 - r0, K), *csr), device=dev)
+    (ids, sel) = _row_ids(A, R, rows, dev)
+    n = _n_selected(sel, R)
+    (Ainv, Kp) = _remapped(Ainv, col_remap, n_cols_phys)
+    csr = _toeplitz_rows(desc, wq, None, ids, n, dev)
+    csr = _keycompile(csr, n, K, A, Ainv, dev, row_scale_slice=sel)
+    return SparseMatrix(((n, Kp), *csr), device=dev)
 
 
-def keyed_linear(weight, bias, A, Ainv, rows=None):
+def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
     """W_hat = A . [[W, b],[0, 1]] . Ainv (keynet/layer.py:69-70)."""
     dev = _device()
     L = _native.lib()
     W = torch.as_tensor(weight).detach().to(device=dev, dtype=torch.float32).contiguous()
     (n_out, n_in) = W.shape
     b = torch.as_tensor(bias).detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
-    (ids, r0, r1) = _row_ids(A, n_out + 1, rows, dev)
-    n = r1 - r0
+    (ids, sel) = _row_ids(A, n_out + 1, rows, dev)
+    n = _n_selected(sel, n_out + 1)
+    (Ainv, Kp) = _remapped(Ainv, col_remap, n_cols_phys)
     csr = _two_phase(
         n,
         lambda row_nnz: check(L.kn_linear_count(ptr(W), ptr(b), n_out, n_in, ptr(ids), n, ptr(row_nnz), stream_ptr())),
         lambda ip, ix, dt: check(L.kn_linear_fill(ptr(W), ptr(b), n_out, n_in, ptr(ids), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
         dev)
-    csr = _keycompile(csr, n, n_in + 1, A, Ainv, dev, row_scale_slice=slice(r0, r1))
-    return SparseMatrix(((n, n_in + 1), *csr), device=dev)
+    csr = _keycompile(csr, n, n_in + 1, A, Ainv, dev, row_scale_slice=sel)
+    return SparseMatrix(((n, Kp), *csr), device=dev)
 
 
 def sparse_toeplitz_conv2d(inshape, f, bias=None, as_correlation=True, stride=1, format='csr'):
