@@ -200,11 +200,11 @@ def time_oracle(layers, inshape, n_images, threads, repeats=1):
     return best
 
 
-def cpu_baseline(layers, inshape, budget_s=12.0):
+def cpu_baseline(layers, inshape, budget_s=15.0):
     from oracle import keynet_oracle as ko
     threads = ko.max_threads()
-    t_probe = time_oracle(layers, inshape, 2, threads)
-    n = int(max(2, min(8192, (budget_s / max(t_probe / 2.0, 1e-6)))))
+    t_probe = time_oracle(layers, inshape, 32, threads)
+    n = int(max(32, min(16384, (budget_s / max(t_probe / 32.0, 1e-6)))))
     dt = time_oracle(layers, inshape, n, threads)
     return {'value': n / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
             'sample': '%d images through the same compiled layer stack, oracle csr_matvecs port (OpenMP over rows), %.1f s' % (n, dt)}
