@@ -73,13 +73,14 @@ int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const fl
  *   kn_pg_pack               rows[n_groups][G] -> cols[n_groups][K_pad], vals[n_groups][G][K_pad] (zero padded)
  *   kn_spmm_pg_f32           Y[rows[g][:], :] = vals[g] . X[cols[g][:], :]  (+ReLU); fp32 FMA, K_pad % 32 == 0,
  *                            n_vecs/ldx/ldy multiples of 4; group_k[g] (nullable) = number of leading columns of group g
- *                            that are real (the rest of K_pad is zero padding and is skipped) */
+ *                            that are real (the rest of K_pad is zero padding and is skipped); block_of[g] (nullable) =
+ *                            index of the group's value block in `vals` when identical blocks are stored once (unique tiles) */
 int kn_csr_row_pattern_hash(const int64_t *indptr, const int32_t *indices, int64_t n_rows, uint64_t *hash, void *stream);
 int kn_pg_verify(const int64_t *indptr, const int32_t *indices, const int64_t *rows, const int64_t *leaders, int64_t n,
                  int32_t *mismatch, void *stream);
 int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data, const int64_t *rows,
                int64_t n_groups, int32_t G, int32_t K_pad, int32_t *cols, float *vals, void *stream);
-int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
+int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
 /* Tensor-core variant (csrc/pgroup_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo),
@@ -90,7 +91,7 @@ int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, 
 #define KN_TENSORMAP_BYTES 128
 int kn_pg_tc_split(const float *vals, int64_t n, float *vals_hi, float *vals_lo, void *stream);
 int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64_t n_rows_total, int32_t G, int32_t K_pad, void *maps_out_host);
-int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
+int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                       const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
 /* ---- prefix sum: out[0]=0, out[i+1]=out[i]+in[i]; out has n+1 entries (in may alias out+1) */

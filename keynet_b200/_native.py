@@ -58,10 +58,10 @@ def lib():
         'kn_csr_row_pattern_hash': [vp, vp, i64, vp, vp],
         'kn_pg_verify': [vp, vp, vp, vp, i64, vp, vp],
         'kn_pg_pack': [vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp],
-        'kn_spmm_pg_f32': [vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
+        'kn_spmm_pg_f32': [vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_pg_tc_split': [vp, i64, vp, vp, vp],
         'kn_pg_tc_tensormaps': [vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp],
-        'kn_spmm_pg_tc_f32': [vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
+        'kn_spmm_pg_tc_f32': [vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_exclusive_scan_i64': [vp, vp, i64, vp],
         'kn_toeplitz_conv2d_count': [ctypes.POINTER(kn_conv2d_desc), vp, i64, vp, vp],
         'kn_toeplitz_conv2d_fill': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, vp],

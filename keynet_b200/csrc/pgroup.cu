@@ -102,7 +102,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int RW, bool RELU>
 __global__ void __launch_bounds__(kThreads, 2)
 pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
-               const int32_t *__restrict__ group_k, int64_t n_groups, int G, int K_pad, int tiles_per_group, int64_t n_items, int64_t n_tiles,
+               const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_groups, int G, int K_pad, int tiles_per_group, int64_t n_items, int64_t n_tiles,
                const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
 {
     constexpr int TM = 8 * RW;
@@ -118,7 +118,8 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
     // groups of one class share K_pad (storage) but loop only over their own K (edge / corner pixels have fewer taps)
     const int n_chunks = group_k ? (__ldg(group_k + g) + KT - 1) / KT : K_pad / KT;
 
-    const float *__restrict__ vbase = vals + (g * G + (int64_t)rowtile * TM) * K_pad;
+    const int64_t blk = block_of ? (int64_t)__ldg(block_of + g) : g;       // unique value block of this group
+    const float *__restrict__ vbase = vals + (blk * G + (int64_t)rowtile * TM) * K_pad;
     const int32_t *__restrict__ cbase = cols + g * (int64_t)K_pad;
     const int rows_here = min(TM, G - rowtile * TM);
 
@@ -203,7 +204,7 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
 template <int GM, bool RELU>
 __global__ void __launch_bounds__(kThreads)
 pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
-                const int32_t *__restrict__ group_k, int64_t n_groups, int G, int K_pad, int64_t n_supers, int tiles_per_super,
+                const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_groups, int G, int K_pad, int64_t n_supers, int tiles_per_super,
                 const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -215,11 +216,12 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
     if (item >= n_groups * n_supers) return;
     const int64_t sup = item / n_groups, g = item - sup * n_groups;
     const int K = group_k ? __ldg(group_k + g) : K_pad;
+    const int64_t blk = block_of ? (int64_t)__ldg(block_of + g) : g;
 
     for (int i = lane; i < K; i += 32) s_col[i] = __ldg(cols + g * (int64_t)K_pad + i);
     for (int i = lane; i < K * GM; i += 32) {
         const int k = i / GM, r = i - k * GM;
-        s_val[i] = (r < G) ? __ldg(vals + (g * G + r) * (int64_t)K_pad + k) : 0.0f;
+        s_val[i] = (r < G) ? __ldg(vals + (blk * G + r) * (int64_t)K_pad + k) : 0.0f;
     }
     __syncwarp();
 
@@ -257,7 +259,7 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
 }
 
 template <int GM>
-int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
+int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
                  const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
     const int tiles_per_super = 16;                                          // 2048 batch columns per warp work item
@@ -271,14 +273,14 @@ int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, co
         KN_CUDA(cudaFuncSetAttribute(pg_small_kernel<GM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         configured = true;
     }
-    if (relu) pg_small_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
-    else      pg_small_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
+    if (relu) pg_small_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
+    else      pg_small_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
 
 template <int RW>
-int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
+int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
     constexpr int TM = 8 * RW;
@@ -293,8 +295,8 @@ int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const
         configured = true;
     }
     dim3 grid((unsigned)(gx * gy));
-    if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
-    else      pg_simt_kernel<RW, false><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
+    if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
+    else      pg_simt_kernel<RW, false><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -335,7 +337,7 @@ KN_API int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float
     return KN_OK;
 }
 
-KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
+KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                           const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KT == 0, "spmm_pg: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg: bad leading dimension");
@@ -345,14 +347,14 @@ KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float 
                "spmm_pg: n_vecs, ldx, ldy must be multiples of 4 and X, Y 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const bool relu = (flags & KN_SPMM_RELU) != 0;
-    if (G <= 8 && K_pad <= 128)  return launch_small<8>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 16 && K_pad <= 128) return launch_small<16>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 8)  return launch_pg<1>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 16) return launch_pg<2>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 32) return launch_pg<4>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    if (G <= 64) return launch_pg<8>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 8 && K_pad <= 128)  return launch_small<8>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 16 && K_pad <= 128) return launch_small<16>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 8)  return launch_pg<1>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 16) return launch_pg<2>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 32) return launch_pg<4>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (G <= 64) return launch_pg<8>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     // pick the row tile (96 or 128) that wastes fewer padded rows
     const int waste96 = ((G + 95) / 96) * 96 - G, waste128 = ((G + 127) / 128) * 128 - G;
-    if (waste96 < waste128) return launch_pg<12>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
-    return launch_pg<16>(rows, cols, vals, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    if (waste96 < waste128) return launch_pg<12>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    return launch_pg<16>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
 }

@@ -121,7 +121,7 @@ __device__ __forceinline__ void tmem_store(uint32_t taddr, const uint32_t (&r)[N
 template <int NB, bool RELU, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-             const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k,
+             const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of,
              int G, int Gp, int K_pad, int chunks_per_group, int64_t n_items, int64_t n_tiles, int n_b, int n_a, uint32_t a0,
              const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
 {
@@ -169,7 +169,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer: weight block planes (hi, lo), 16 k x Gp rows per stage =====
         if (lane == 0) {
-            const int grow = (int)(g * G) + row0;
+            const int grow = (int)((block_of ? (int64_t)__ldg(block_of + g) : g) * G) + row0;      // rows of the group's unique value block
             for (int ks = 0; ks < n_ksteps; ks++) {
                 const int s = ks % n_b;
                 const uint32_t ph = (uint32_t)(ks / n_b) & 1u;
@@ -355,7 +355,7 @@ PFN_encodeTiled get_encode() {
 }
 
 template <int NB, bool DUAL>
-int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int G, int K_pad,
+int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
     const int chunks_per_group = (G + 255) / 256;
@@ -377,8 +377,8 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
         configured = true;
     }
     dim3 grid((unsigned)(gx * gy));
-    if (relu) pg_tc_kernel<NB, true, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
-    else      pg_tc_kernel<NB, false, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
+    if (relu) pg_tc_kernel<NB, true, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
+    else      pg_tc_kernel<NB, false, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -415,7 +415,7 @@ KN_API int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64
     return KN_OK;
 }
 
-KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, int64_t n_groups, int32_t G, int32_t K_pad,
+KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                              const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KS == 0, "spmm_pg_tc: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg_tc: bad leading dimension");
@@ -429,10 +429,10 @@ KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const i
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
     // two batch tiles per CTA share every weight stage when accumulators + a >= 2-deep activation ring fit TMEM
     if (Gp <= 96 && n_vecs > BM)          // 2 tiles x 2*Gp accumulator columns + a 2-deep activation ring fit the 512 TMEM columns
-        return launch_tc<2, true>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+        return launch_tc<2, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
     if (Gp <= 128)
-        return launch_tc<1, true>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+        return launch_tc<1, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
     if (2 * Gp + 2 * 64 <= 512 && n_vecs > BM)
-        return launch_tc<2, false>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
-    return launch_tc<1, false>(maps, rows, cols, group_k, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+        return launch_tc<2, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    return launch_tc<1, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
 }

@@ -397,6 +397,55 @@ def tensor_cores_enabled(flag=None):
     return _TC['enabled']
 
 
+def _dedup_value_blocks(cols, vals, group_k, ng, G, K_pad, chunk_bytes=1 << 30):
+    """Store identical value blocks once (the reference's unique tiles, keynet/sparse.py:553-568,690-779).
+
+    Two groups hold the same block only up to the order of their columns (each group lists its columns by ascending
+    permuted index), so every group's columns are first put in a canonical order -- sorted by a 64-bit signature of
+    the column's G values, padding last -- with `cols` permuted alongside; blocks are then hashed, grouped with
+    torch.unique and VERIFIED element-wise against their representative.  Returns (cols, vals_unique, block_of) or the
+    inputs unchanged with block_of=None when nothing is shared.  Build-time plumbing on torch device ops."""
+    dev = vals.device
+    v3 = vals.view(ng, G, K_pad)
+    c2 = cols.view(ng, K_pad)
+    rw = (torch.arange(G, device=dev, dtype=torch.int64) * 0x9E3779B1 + 0x7F4A7C15) | 1          # odd per-row weights
+    kw = (torch.arange(K_pad, device=dev, dtype=torch.int64) * 0x85EBCA77 + 0x165667B1) | 1      # odd per-column weights
+    step = max(1, int(chunk_bytes // (G * K_pad * 8)))
+    blk_hash = torch.empty(ng, dtype=torch.int64, device=dev)
+    big = torch.iinfo(torch.int64).max
+    karange = torch.arange(K_pad, device=dev).view(1, K_pad)
+    for g0 in range(0, ng, step):
+        g1 = min(ng, g0 + step)
+        vi = v3[g0:g1].view(torch.int32).to(torch.int64)                                          # bit patterns
+        sig = (vi * rw.view(1, G, 1)).sum(dim=1)                                                   # [n, K_pad] column signatures
+        sig = torch.where(karange < group_k[g0:g1].view(-1, 1), sig, torch.full_like(sig, big))   # padding columns last
+        order = torch.argsort(sig, dim=1, stable=True)
+        c2[g0:g1] = torch.gather(c2[g0:g1], 1, order)
+        v3[g0:g1] = torch.gather(v3[g0:g1], 2, order.view(-1, 1, K_pad).expand(-1, G, -1))
+        vi = v3[g0:g1].view(torch.int32).to(torch.int64)
+        blk_hash[g0:g1] = ((vi * rw.view(1, G, 1)).sum(dim=1) * kw.view(1, K_pad)).sum(dim=1) + group_k[g0:g1].to(torch.int64) * 0x27D4EB2F
+        del vi, sig, order
+    (uniq, inverse) = torch.unique(blk_hash, return_inverse=True)
+    nu = int(uniq.numel())
+    if nu == ng:
+        return (cols, vals, None)
+    # representative = first group of every hash value; verify every group against its representative
+    first = torch.full((nu,), ng, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inverse, torch.arange(ng, device=dev), reduce='amin')
+    rep = first[inverse]
+    ok = True
+    for g0 in range(0, ng, step):
+        g1 = min(ng, g0 + step)
+        if not bool(torch.equal(v3[g0:g1].view(torch.int32), v3[rep[g0:g1]].view(torch.int32))):
+            ok = False
+            break
+    if not ok:
+        warnings.warn('value-block hash collision: blocks of this class are stored per group')
+        return (cols, vals, None)
+    vals_u = v3[first].contiguous().view(-1)
+    return (cols, vals_u, inverse.to(torch.int32).contiguous())
+
+
 class PatternGroups(object):
     """Rows with an identical column set, packed as dense value blocks (see csrc/pgroup.cu).
 
@@ -418,7 +467,7 @@ class PatternGroups(object):
         self.padded_values = 0
 
     @staticmethod
-    def build(W, min_group=4, max_pad_waste=0.25):
+    def build(W, min_group=4, max_pad_waste=0.25, dedup=True):
         """max_pad_waste: a class is split when a group's K falls below this fraction of the class maximum."""
         L = _native.lib()
         dev = W._data.device
@@ -474,19 +523,23 @@ class PatternGroups(object):
                 cols = torch.empty(ng * K_pad, dtype=torch.int32, device=dev)
                 vals = torch.empty(ng * G * K_pad, dtype=torch.float32, device=dev)
                 check(L.kn_pg_pack(ptr(indptr), ptr(indices), ptr(data), ptr(rows64), ng, int(G), K_pad, ptr(cols), ptr(vals), stream_ptr()))
+                group_k = K[g_sub].to(torch.int32).contiguous()
+                block_of = None
+                if dedup and ng > 1:
+                    (cols, vals, block_of) = _dedup_value_blocks(cols, vals, group_k, ng, int(G), K_pad)
                 cls = dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals, tc=None,
-                           group_k=K[g_sub].to(torch.int32).contiguous())
+                           group_k=group_k, block_of=block_of, n_blocks=ng if block_of is None else int(vals.numel() // (int(G) * K_pad)))
                 if int(G) >= PatternGroups.TC_MIN_G and PatternGroups.TC_MIN_K <= K_pad <= PatternGroups.TC_MAX_K and tensor_cores_enabled():
                     # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
                     (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
                     check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
                     maps = ctypes.create_string_buffer(2 * 128)
-                    check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), ng * int(G), int(G), K_pad, maps))
+                    check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * int(G), int(G), K_pad, maps))
                     cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
                 pg.classes.append(cls)
                 in_group[rows64] = True
                 pg.grouped_rows += ng * int(G)
-                pg.padded_values += ng * int(G) * K_pad
+                pg.padded_values += cls['n_blocks'] * int(G) * K_pad
         rest_rows = torch.nonzero(~in_group).reshape(-1)
         if rest_rows.numel() > 0:
             n = int(rest_rows.numel())
@@ -506,10 +559,10 @@ class PatternGroups(object):
         flags = _native.KN_SPMM_RELU if relu else 0
         for c in self.classes:
             if c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
-                check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), c['n_groups'], c['G'], c['K_pad'],
+                check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
                                           ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
             else:
-                check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), ptr(c['group_k']), c['n_groups'], c['G'], c['K_pad'],
+                check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
                                        ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
         r = self.rest
         if r is not None:
@@ -520,7 +573,7 @@ class PatternGroups(object):
         return len(self.classes) + (1 if self.rest is not None else 0)
 
     def summary(self):
-        return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], tensor_core=[c['tc'] is not None for c in self.classes], grouped_rows=self.grouped_rows,
+        return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], unique_blocks=[c['n_blocks'] for c in self.classes], tensor_core=[c['tc'] is not None for c in self.classes], grouped_rows=self.grouped_rows,
                     rest_rows=0 if self.rest is None else self.rest['n'], padded_values=self.padded_values)
 
 

@@ -462,3 +462,33 @@ def test_pattern_groups_tensor_core_path(M, C, N):
     y2 = sparse.spmm(W, Xd, relu=False).cpu().numpy()
     sparse.PatternGroups.TC_MIN_K = 128
     assert _close(y2, ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=False, threads=8))
+
+
+def test_unique_value_blocks_under_permutation_keys():
+    """Permutation keys only relabel rows/columns, so all interior output pixels share one value block (the reference's
+    unique tiles, but also under a GLOBAL permutation where its TiledMatrix cannot be used, system.py:360): a 3x3 conv
+    has 9 distinct blocks (interior, 4 edges, 4 corners); gain keys make every block different."""
+    from keynet_b200 import sparse
+    ko = _ko()
+    rs = np.random.RandomState(4)
+    (C, U, V, M, N) = (4, 9, 11, 32, 256)
+    f = rs.randn(M, C, 3, 3).astype(np.float32); b = rs.randn(M).astype(np.float32)
+    perm = lambda n: sparse.MonomialKey(np.concatenate([rs.permutation(n - 1), [n - 1]]))
+    gain = lambda n: sparse.MonomialKey(np.arange(n), np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32))
+    X = rs.randn(C * U * V + 1, N).astype(np.float32); X[-1] = 1.0
+    for (A, Ainv, expect_unique) in [(None, perm(C * U * V + 1), 9), (perm(M * U * V + 1), perm(C * U * V + 1), None), (None, gain(C * U * V + 1), U * V)]:
+        W = sparse.keyed_toeplitz_conv2d((C, U, V), f, b, 1, A, Ainv)
+        assert W._pg is not None and len(W._pg.classes) == 1
+        s = W._pg.summary()
+        assert s['classes'][0][0] == M and s['classes'][0][2] == U * V
+        if expect_unique is not None:
+            assert s['unique_blocks'][0] == expect_unique, s
+        (ip, ix, dt) = W.csr_arrays()
+        ref = ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=True, threads=8)
+        for tc in (True, False):
+            sparse.tensor_cores_enabled(tc)
+            try:
+                y = sparse.spmm(W, torch.from_numpy(X).cuda(), relu=True).cpu().numpy()
+            finally:
+                sparse.tensor_cores_enabled(True)
+            assert _close(y, ref), (tc, np.abs(y - ref).max())
