@@ -24,7 +24,7 @@ class FusedReLU(nn.Module):
 
 
 class KeyedLayer(nn.Module):
-    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None, col_remap=None, n_cols_phys=None):
+    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None, col_remap=None, n_cols_phys=None, keep_csr=True):
         """module: nn.Conv2d | nn.AvgPool2d | nn.Linear | nn.ReLU; A / Ainv: MonomialKey (A may be None for the
         last layer); rows=(r0, r1) or an index array: build and hold only those rows of W_hat (row shard);
         col_remap / n_cols_phys: physical position of every canonical input column (gathered layout, dist.py)."""
@@ -83,6 +83,9 @@ class KeyedLayer(nn.Module):
         if tileshape is not None:
             from .tiled import tile_keyed_layer
             self.W = tile_keyed_layer(self.W, module, inshape, outshape, tileshape)
+        if not keep_csr and getattr(self.W, '_pg', None) is not None:
+            self.W.drop_csr()
+            torch.cuda.empty_cache()
         if verbose():
             torch.cuda.synchronize()
             print('[KeyedLayer]: %s compiled on GPU in %1.3f seconds, nnz=%d' % (self._repr, time.time() - t0, self.nnz()))

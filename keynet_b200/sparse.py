@@ -259,7 +259,18 @@ class SparseMatrix(object):
         return SparseMatrix((self.shape, self._indptr.clone(), self._indices.clone(), self._data.clone()), device=self._data.device)
 
     def nnz(self):
-        return int(self._data.numel()) if self._data is not None else 0
+        if self._data is None:
+            return int(getattr(self, '_nnz', 0))
+        return int(self._data.numel())
+
+    def drop_csr(self):
+        """Free the canonical CSR and keep only the pattern-grouped execution format (VGG16-scale layers: 120 GB of
+        CSR vs < 1 GB of unique value blocks + gather lists).  The matrix can no longer be exported or row-sliced."""
+        assert self._pg is not None, 'drop_csr() needs the pattern-grouped format'
+        self._nnz = self.nnz()
+        self._device = self._data.device
+        (self._indptr, self._indices, self._data) = (None, None, None)
+        return self
 
     def from_torch_dense(self, A):
         """Non-zero entries of a dense matrix, row-major (scipy coo_matrix(dense) semantics)."""
@@ -291,7 +302,7 @@ class SparseMatrix(object):
         Replaces keynet/sparse.py:488-492.  A transposed view of a feature-major activation (what
         KeyedLayer.forward passes) is consumed without a copy; CPU tensors are staged through the GPU."""
         assert x_torch.ndim == 2 and x_torch.shape[0] == self.shape[1], "Non-conformal shape for W=%s, x=%s" % (str(self.shape), str(tuple(x_torch.shape)))
-        dev = self._data.device
+        dev = self._data.device if self._data is not None else self._device
         on_host = not x_torch.is_cuda
         x = x_torch.detach()
         if x.dtype != torch.float32:
@@ -589,6 +600,15 @@ def spmm(W, x, relu=False, out=None):
     assert y.shape == (R, N) and y.is_contiguous()
     if W._pg is not None and N >= 32 and N % 4 == 0:
         W._pg.spmm(x, y, relu)
+        return y
+    if W._data is None:
+        # CSR was dropped (drop_csr): narrow / ragged batches are padded to the grouped kernels' granularity
+        Np = max(32, (N + 3) // 4 * 4)
+        xp = torch.zeros((x.shape[0], Np), dtype=torch.float32, device=x.device)
+        xp[:, :N] = x
+        yp = torch.empty((R, Np), dtype=torch.float32, device=x.device)
+        W._pg.spmm(xp, yp, relu)
+        y.copy_(yp[:, :N])
         return y
     check(_native.lib().kn_spmm_csr_f32(ptr(W._indptr), ptr(W._indices), ptr(W._data), R, W.shape[1],
                                         ptr(x), N, ptr(y), N, N, _native.KN_SPMM_RELU if relu else 0, stream_ptr()))

@@ -256,7 +256,7 @@ class PublicKeyedSensor(KeyedSensor):
 
 
 # =============================================================================================
-def layergen(module, inshape, outshape, A, Ainv, tileshape=None, backend='b200', rows=None):
+def layergen(module, inshape, outshape, A, Ainv, tileshape=None, backend='b200', rows=None, keep_csr=True):
     """Keyed-layer factory (keynet/system.py:303-314).  tileshape is snapped to divisors of the spatial size;
     the only backend is 'b200' ('scipy' is accepted as an alias so reference call sites keep working)."""
     if tileshape is not None:
@@ -265,7 +265,7 @@ def layergen(module, inshape, outshape, A, Ainv, tileshape=None, backend='b200',
             print('[layergen]: Ragged spatial tileshape=%s, forcing non-ragged tileshape "%s" for inshape="%s", outshape="%s"' % (str(tileshape), str(new_tileshape), str(inshape), str(outshape)))
         tileshape = new_tileshape
     if backend in ('b200', 'scipy'):
-        return _layer.KeyedLayer(module, inshape, outshape, A, Ainv, tileshape=tileshape, rows=rows)
+        return _layer.KeyedLayer(module, inshape, outshape, A, Ainv, tileshape=tileshape, rows=rows, keep_csr=keep_csr)
     raise ValueError('invalid backend "%s"' % backend)
 
 
@@ -400,10 +400,12 @@ def keypair_policy(global_photometric='identity', local_photometric='identity', 
 
 
 def Keynet(inshape, net=None, backend='b200', global_photometric='identity', local_photometric='identity', global_geometric='identity', local_geometric='identity', memoryorder='channel',
-           do_output_encryption=False, alpha=None, beta=None, gamma=None, hierarchical_blockshape=None, hierarchical_permute_at_level=None, blocksize=None, tileshape=None):
+           do_output_encryption=False, alpha=None, beta=None, gamma=None, hierarchical_blockshape=None, hierarchical_permute_at_level=None, blocksize=None, tileshape=None,
+           keep_csr=True):
     """(sensor, model) for a plain torch net (keynet/system.py:472-486).  Output keys of layers named '*relu*'
     are restricted to keys that commute with ReLU: no global transforms, local gain / local permutation only."""
-    f_layergen = lambda module, inshape, outshape, A, Ainv: layergen(module, inshape, outshape, A, Ainv, tileshape=tileshape, backend=backend)
+    # keep_csr=False (not in the reference): free each layer's canonical CSR once its pattern-grouped form exists
+    f_layergen = lambda module, inshape, outshape, A, Ainv: layergen(module, inshape, outshape, A, Ainv, tileshape=tileshape, backend=backend, keep_csr=keep_csr)
     f_keypair = keypair_policy(global_photometric=global_photometric, local_photometric=local_photometric, global_geometric=global_geometric, local_geometric=local_geometric,
                                memoryorder=memoryorder, alpha=alpha, beta=beta, gamma=gamma, hierarchical_blockshape=hierarchical_blockshape,
                                hierarchical_permute_at_level=hierarchical_permute_at_level, blocksize=blocksize, tileshape=tileshape)
