@@ -54,6 +54,9 @@ def workload(name):
     if name == 'lenet':
         return dict(net=numpy_weights(nets.LeNet_AvgPool(), 0).eval(), inshape=(1, 28, 28), keys=dict(global_geometric='permutation'),
                     label='LeNet_AvgPool 1x28x28, PermutationKeynet (BASELINE configs[0])')
+    if name == 'vgg16':
+        return dict(net=numpy_weights(nets.VGG16(), 0).eval(), inshape=(3, 224, 224), keys=dict(global_geometric='permutation', keep_csr=False),
+                    label='VGG16 3x224x224, PermutationKeynet, pattern groups with unique value blocks on one GPU (BASELINE configs[3])')
     raise ValueError(name)
 
 
@@ -242,7 +245,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=4096, help='images per GPU per step')
-    ap.add_argument('--net', default='acn', choices=['acn', 'lenet'])
+    ap.add_argument('--net', default='acn', choices=['acn', 'lenet', 'vgg16'])
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -356,11 +359,11 @@ def main():
                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': wl['label'], 'batch_per_gpu': N, 'global_batch': N * world, 'parallelism': 'dp%d replicas, no collective' % world,
                           'l2': 'inputs larger than L2: %.2f GB of CSR + %.2f GB of activations per step' % (sum(L[1].nnz() for L in plan.layers) * 8 / 1e9, sum((L[1].shape[0] + L[1].shape[1]) * N * 4 for L in plan.layers) / 1e9),
-                          'nnz': int(sum(L[1].nnz() for L in plan.layers)), 'key_compile_s': round(t_compile, 3)},
+                          'nnz': int(sum(L[1].nnz() for L in plan.layers)), 'key_compile_s': round(t_compile, 3), 'hbm_allocated_gb': round(torch.cuda.max_memory_allocated() / 1e9, 2)},
                'e2e': {'value': world * N * K / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(host_in.numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4 + 4),
                        'ms_per_step': ms_e2e / K},
                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.net != 'vgg16':     # the oracle cannot hold 120 GB of CSR on the host
             out['cpu_baseline'] = cpu_baseline(oracle_layers_from_gpu(sensor, knet), wl['inshape'])
         print(json.dumps(out))
     if world > 1:

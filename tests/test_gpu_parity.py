@@ -492,3 +492,52 @@ def test_unique_value_blocks_under_permutation_keys():
             finally:
                 sparse.tensor_cores_enabled(True)
             assert _close(y, ref), (tc, np.abs(y - ref).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# TiledMatrix / Conv2dTiledMatrix structure (reference keynet/sparse.py:517-835, test/test_sparse.py:122)
+def test_tiled_matrix_structure_matches_reference():
+    from keynet_b200 import sparse, tiled
+    z = gu.load('tiled_kat.npz')
+    # avgpool (2,8,8), identity keys, tiles (4,8)
+    W = sparse.keyed_toeplitz_avgpool2d((2, 8, 8), 3, 2, sparse.sparse_identity_matrix(2 * 16 + 1), sparse.sparse_identity_matrix(2 * 64 + 1))
+    _assert_bit_exact(W, *gu.csr_arrays(z, 'pool.W'), what='pool W')
+    T = tiled.TiledMatrix(W, tuple(int(t) for t in z['pool.tileshape']))
+    assert np.array_equal(np.array(T.blocks(), dtype=np.int64), z['pool.blocks'])
+    assert len(T.tiles()) == int(z['pool.ntiles']) and T.nnz() == int(z['pool.nnz'])
+    E = T.tocsr(); E.sort_indices()
+    (shape, ip, ix, dt) = gu.csr_arrays(z, 'pool.expanded')
+    assert E.shape == shape and np.array_equal(E.indptr, ip) and np.array_equal(E.indices, ix) and np.array_equal(E.data, dt)
+    assert sum(t.nnz for t in T.tiles()) == T.nnz() and T.tileshape() == (4, 8)
+    # conv (3,8,8)->(4,8,8), identity keys, tiles (4,4), with bias column
+    inshape = tuple(int(s) for s in z['conv.inshape']); outshape = tuple(int(s) for s in z['conv.outshape'])
+    Wc = sparse.keyed_toeplitz_conv2d(inshape, z['conv.f'], z['conv.b'], 1, sparse.sparse_identity_matrix(int(np.prod(outshape)) + 1), sparse.sparse_identity_matrix(int(np.prod(inshape)) + 1))
+    _assert_bit_exact(Wc, *gu.csr_arrays(z, 'conv.W'), what='conv W')
+    Tc = tiled.Conv2dTiledMatrix(Wc, inshape, outshape, tuple(int(t) for t in z['conv.tileshape']), bias=True, sanitycheck=False)
+    assert np.array_equal(np.array(Tc.blocks(), dtype=np.int64), z['conv.blocks'])
+    assert Tc.nnz() == int(z['conv.nnz']) and Tc._n_tile_entries == int(z['conv.ntile_entries'])
+    y = Tc.torchdot(torch.from_numpy(z['conv.x'])).numpy()
+    assert _close(y, z['conv.y'])
+    with pytest.raises(AssertionError):
+        Tc.torchdot(torch.zeros(5, 2))
+
+
+def test_tiled_keynets_match_plain_net():
+    """reference test_keynet.py:37 (tiled identity keynet) and TiledPermutationKeynet: keyed == plain, atol 1e-5."""
+    from keynet_b200 import system, nets, tiled
+    torch.manual_seed(2)
+    net = nets.LeNet_AvgPool().eval()
+    x = torch.randn(3, 1, 28, 28)
+    yp = net(x).detach().numpy()
+    (sensor, knet) = system.Keynet((1, 28, 28), net, tileshape=(28, 28))
+    assert any(isinstance(L.W, tiled.Conv2dTiledMatrix) for (k, L) in knet.keyedlayers())
+    y = knet.forward(sensor.fromtensor(x).encrypt().astensor()).reshape(3, -1).numpy()
+    assert np.allclose(y, yp, atol=1e-5)
+    (s0, k0) = system.Keynet((1, 28, 28), net)
+    assert knet.num_parameters() < k0.num_parameters()          # unique-tile storage is smaller than the expanded matrices
+    np.random.seed(3)
+    (sensor, knet) = system.TiledPermutationKeynet((1, 28, 28), net, 4)
+    y = knet.forward(sensor.fromtensor(x).encrypt().astensor()).reshape(3, -1).numpy()
+    assert np.allclose(y, yp, atol=1e-5)
+    # local (block-repeated) permutation keys keep the matrices tile compressible
+    assert knet.num_parameters() < k0.num_parameters()
