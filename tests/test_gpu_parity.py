@@ -541,3 +541,25 @@ def test_tiled_keynets_match_plain_net():
     assert np.allclose(y, yp, atol=1e-5)
     # local (block-repeated) permutation keys keep the matrices tile compressible
     assert knet.num_parameters() < k0.num_parameters()
+
+
+def test_save_and_load_compiled_keynet(tmp_path):
+    """a compiled keynet round-trips through a flat tensor file (no pickled classes, no recompilation)."""
+    from keynet_b200 import system, nets, io
+    torch.manual_seed(5)
+    net = nets.LeNet_AvgPool().eval()
+    np.random.seed(5)
+    (sensor, knet) = system.Keynet((1, 28, 28), net, global_geometric='permutation', global_photometric='uniform_random_gain', beta=1.0)
+    x = torch.randn(40, 1, 28, 28)
+    y = knet.forward(sensor.fromtensor(x).encrypt().astensor()).reshape(40, -1).numpy()
+    p = io.save(str(tmp_path / 'lenet.keynet'), sensor, knet)
+    (s2, k2) = io.load(p)
+    assert [k for (k, _) in k2.keyedlayers()] == [k for (k, _) in knet.keyedlayers()] and k2.num_parameters() == knet.num_parameters()
+    for ((_, a), (_, b)) in zip(knet.keyedlayers(), k2.keyedlayers()):
+        _assert_bit_exact(b.W, a.W.shape, *a.W.csr_arrays())
+    y2 = k2.forward(s2.fromtensor(x).encrypt().astensor()).reshape(40, -1).numpy()
+    assert np.array_equal(y, y2)
+    # public release: keys removed, the keyed network still runs on ciphertext
+    xc = sensor.fromtensor(x).encrypt().astensor()
+    (s3, k3) = io.load(io.save(str(tmp_path / 'public.keynet'), None, knet.public()))
+    assert s3 is None and np.array_equal(k3.forward(xc).reshape(40, -1).numpy(), y)
