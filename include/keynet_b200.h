@@ -85,14 +85,19 @@ int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, 
 
 /* Tensor-core variant (csrc/pgroup_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo),
  * fp32 accumulators in TMEM, weight blocks by TMA, gathered activations written into the UMMA layout by producer
- * warps.  kn_pg_tc_split: vals -> (hi = v & 0xffffe000, lo = v - hi); kn_pg_tc_tensormaps: writes two CUtensorMap
- * (2 x 128 bytes, HOST memory) describing the hi / lo planes [n_rows_total][K_pad]; kn_spmm_pg_tc_f32: same contract
+ * warps.  kn_pg_tc_split: vals -> (hi = v & 0xffffe000, lo = v - hi); kn_pg_tc_tensormaps: writes four CUtensorMap
+ * (4 x 128 bytes, HOST memory) describing the hi / lo planes [n_rows_total][K_pad] (full boxes, and half boxes for the
+ * 2-CTA multicast launch); kn_spmm_pg_tc_f32: same contract
  * as kn_spmm_pg_f32 (results agree with fp32 FMA to ~1e-6 relative). */
 #define KN_TENSORMAP_BYTES 128
 int kn_pg_tc_split(const float *vals, int64_t n, float *vals_hi, float *vals_lo, void *stream);
 int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64_t n_rows_total, int32_t G, int32_t K_pad, void *maps_out_host);
 int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                       const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+
+/* debug aid: record clock64 phase stamps (entry, prologue, first stage, last MMA issue, accumulators ready, epilogue
+ * stored, teardown) of CTA `cta` of the next kn_spmm_pg_tc_f32 launches (-1 = off); out_host (nullable) receives 8 values. */
+int kn_debug_tc_timing(int32_t cta, int64_t *out_host);
 
 /* ---- prefix sum: out[0]=0, out[i+1]=out[i]+in[i]; out has n+1 entries (in may alias out+1) */
 int kn_exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, void *stream);

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -74,6 +75,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -118,7 +132,13 @@ __device__ __forceinline__ void tmem_store(uint32_t taddr, const uint32_t (&r)[N
 // A tf32 UMMA with N = 96 needs 4 KB of A and 3 KB of B per 48 cycles; with A in shared memory that is 146 B/clk, above
 // the 128 B/clk shared-memory port, so the tensor pipe starves.  From TMEM the A operand costs no shared-memory
 // bandwidth and the producers' stores (tcgen05.st) bypass shared memory as well.
-template <int NB, bool RELU, bool DUAL>
+// phase timestamps of one CTA (debug aid, read back with kn_debug_tc_timing): entry, prologue done, first stage full,
+// last MMA issued, accumulators ready, epilogue stored, teardown
+__device__ long long g_tc_timing[8];
+__device__ int g_tc_timing_cta = -1;
+#define KN_STAMP(i) do { if ((int)blockIdx.x == g_tc_timing_cta) g_tc_timing[i] = clock64(); } while (0)
+
+template <int NB, bool RELU, bool DUAL, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
              const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of,
@@ -145,13 +165,17 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     const int64_t nbase = rt.tile * (BM * NB);
     // groups of one class share K_pad (storage) but loop only over their own K (edge / corner pixels have fewer taps)
     const int n_ksteps = group_k ? (__ldg(group_k + g) + KS - 1) / KS : K_pad / KS;
+    const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
     // DUAL (Gp <= 128): the hi and lo weight planes are adjacent in shared memory, so ONE UMMA with N = 2*Gp computes
     // x_hi.[w_hi ; w_lo] into two accumulator blocks (summed in the epilogue): 2 instructions per k-step instead of 3.
     const int acc_w = DUAL ? 2 * Gp : Gp;                        // accumulator columns per batch tile
 
+    if (tid == 0) KN_STAMP(0);
     if (warp == 0 && lane == 0) {
         // NB MMA issuers (one per batch tile): each commits once per stage to both rings and once to accum_bar
-        for (int s = 0; s < n_b; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NB); }
+        // CS > 1: the CTAs of a cluster (same group, adjacent batch tiles) share every weight stage by TMA multicast, so a
+        // stage is free only when the issuers of ALL cluster CTAs have retired it
+        for (int s = 0; s < n_b; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NB * CS); }
         for (int s = 0; s < n_a; s++) { mbar_init(&fullA[s], kProducerThreads); mbar_init(&emptyA[s], NB); }
         mbar_init(accum_bar, NB);
         fence_barrier_init();
@@ -163,21 +187,30 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     for (int i = tid; i < n_ksteps * KS; i += kThreads) s_cols[i] = __ldg(cols + g * (int64_t)K_pad + i);
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();                              // partner barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) KN_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer: weight block planes (hi, lo), 16 k x Gp rows per stage =====
         if (lane == 0) {
             const int grow = (int)((block_of ? (int64_t)__ldg(block_of + g) : g) * G) + row0;      // rows of the group's unique value block
+            int s = 0; uint32_t ph = 0;                          // ring position / phase kept incrementally (no runtime div/mod)
             for (int ks = 0; ks < n_ksteps; ks++) {
-                const int s = ks % n_b;
-                const uint32_t ph = (uint32_t)(ks / n_b) & 1u;
                 mbar_wait(&emptyB[s], ph ^ 1u);
                 unsigned char *bs = smem + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&fullB[s], 2u * (uint32_t)b_plane_bytes);
-                tma_load_2d(bs, &map_hi, ks * KS, grow, &fullB[s]);
-                tma_load_2d(bs + b_plane_bytes, &map_lo, ks * KS, grow, &fullB[s]);
+                if (CS == 1) {
+                    tma_load_2d(bs, &map_hi, ks * KS, grow, &fullB[s]);
+                    tma_load_2d(bs + b_plane_bytes, &map_lo, ks * KS, grow, &fullB[s]);
+                } else {
+                    // this CTA fetches rows [rank*Gp/CS, (rank+1)*Gp/CS) of both planes and multicasts them to the cluster
+                    const int part = Gp / CS, r0 = (int)crank * part;
+                    tma_load_2d_mcast(bs + r0 * KS * 4, &map_hi, ks * KS, grow + r0, &fullB[s], (uint16_t)((1u << CS) - 1u));
+                    tma_load_2d_mcast(bs + b_plane_bytes + r0 * KS * 4, &map_lo, ks * KS, grow + r0, &fullB[s], (uint16_t)((1u << CS) - 1u));
+                }
+                if (++s == n_b) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1 || (warp == 3 && NB == 2)) {
@@ -191,11 +224,12 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             const uint32_t idesc2 = make_idesc(BM, 2 * Gp);
             const uint32_t d = tmem_base + (uint32_t)(b * acc_w);
             const uint64_t desc0 = make_desc(smem_u32(smem), 16, 512, kLayoutSW64);
+            int sb = 0, sa = 0; uint32_t pb = 0, pa = 0;
             for (int ks = 0; ks < n_ksteps; ks++) {
-                const int sb = ks % n_b, sa = ks % n_a;
-                mbar_wait(&fullB[sb], (uint32_t)(ks / n_b) & 1u);
-                mbar_wait(&fullA[sa], (uint32_t)(ks / n_a) & 1u);
+                mbar_wait(&fullB[sb], pb);
+                mbar_wait(&fullA[sa], pa);
                 tc_fence_after();
+                if (ks == 0 && warp == 1) KN_STAMP(2);
                 const uint32_t ta = tmem_base + a0 + (uint32_t)((sa * NB + b) * 32);
                 // B: K-major SW64 (64-byte rows), 8-row groups 512 B apart; stage / plane / k-step only move the
                 // 14-bit start-address field (units of 16 B), so the descriptor is one 64-bit add away from desc0
@@ -213,10 +247,14 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                         umma_tf32_ts(d, ta + kk * 8, db_lo, idesc, 1u);                            // x_hi . w_lo
                     }
                 }
-                umma_commit(&emptyB[sb]);                      // both rings are released when every issuer's MMAs retire
+                if (CS == 1) umma_commit(&emptyB[sb]);         // both rings are released when every issuer's MMAs retire
+                else umma_commit_mcast(&emptyB[sb], (uint16_t)((1u << CS) - 1u));
                 umma_commit(&emptyA[sa]);
+                if (++sb == n_b) { sb = 0; pb ^= 1u; }
+                if (++sa == n_a) { sa = 0; pa ^= 1u; }
             }
             umma_commit(accum_bar);
+            if (warp == 1) KN_STAMP(3);
         }
     } else if (warp >= 4) {
         // ===== A producers: gather X, split hi/lo, tcgen05.st into the TMEM A ring =====
@@ -230,8 +268,10 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         const int k0 = (NB == 2) ? 0 : sel * 8;
         const int64_t n = nbase + b_mine * BM + q * 32 + lane;
         const bool n_ok = n < n_vecs;
-        const float *__restrict__ xn = X + (n_ok ? n : 0);
-        const uint32_t ldx32 = (uint32_t)ldx;
+        // address of X[c][n] = xaddr + c * (ldx * 4): one IMAD.WIDE.U32 + one ld.global.nc per element.  Batch lanes past
+        // n_vecs are clamped to the last valid column: their TMEM rows only feed outputs the epilogue never stores.
+        const uint64_t xaddr = reinterpret_cast<uint64_t>(X) + (uint64_t)(n_ok ? n : (n_vecs - 1)) * 4ull;
+        const uint32_t ldxb = (uint32_t)ldx * 4u;
         float buf[PD][KW];
 
         auto gather = [&](float (&v)[KW], int ks) {
@@ -239,22 +279,25 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 #pragma unroll
             for (int i4 = 0; i4 < KW / 4; i4++) {
                 const int4 c = cp[i4];                          // warp-broadcast LDS.128: 4 column indices
-                // one IMAD.WIDE.U32 per address (row index and leading dimension are both < 2^32)
-                v[4 * i4 + 0] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.x * ldx32) : 0.0f;
-                v[4 * i4 + 1] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.y * ldx32) : 0.0f;
-                v[4 * i4 + 2] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.z * ldx32) : 0.0f;
-                v[4 * i4 + 3] = n_ok ? __ldg(xn + (uint64_t)(uint32_t)c.w * ldx32) : 0.0f;
+                const uint32_t cc[4] = {(uint32_t)c.x, (uint32_t)c.y, (uint32_t)c.z, (uint32_t)c.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint64_t a;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cc[j]), "r"(ldxb), "l"(xaddr));
+                    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v[4 * i4 + j]) : "l"(a));
+                }
             }
         };
-        auto publish = [&](const float (&v)[KW], int ks) {
-            const int sa = ks % n_a;
+        int psa = 0; uint32_t ppa = 0;                           // producer ring position / phase
+        auto publish = [&](const float (&v)[KW]) {
+            const int sa = psa;
             uint32_t hi[KW], lo[KW];
 #pragma unroll
             for (int i = 0; i < KW; i++) {
                 hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
                 lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
             }
-            mbar_wait(&emptyA[sa], ((uint32_t)(ks / n_a) & 1u) ^ 1u);
+            mbar_wait(&emptyA[sa], ppa ^ 1u);
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a0 + (uint32_t)((sa * NB + b_mine) * 32 + k0);
             tmem_store<KW>(ta, hi);
@@ -262,10 +305,11 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         };
         // completing a stage (wait for the TMEM stores, then signal the issuers) is deferred until the next
         // gather has been issued, so the store latency overlaps with load issue instead of serialising every stage
-        auto finish = [&](int ks) {
+        auto finish = [&]() {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&fullA[ks % n_a]);
+            mbar_arrive(&fullA[psa]);
+            if (++psa == n_a) { psa = 0; ppa ^= 1u; }
         };
 #pragma unroll
         for (int d = 0; d < PD; d++)
@@ -275,9 +319,9 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             for (int d = 0; d < PD; d++) {
                 const int ks = ks0 + d;
                 if (ks < n_ksteps) {
-                    publish(buf[d], ks);
+                    publish(buf[d]);
                     if (ks + PD < n_ksteps) gather(buf[d], ks + PD);
-                    finish(ks);
+                    finish();
                 }
             }
         }
@@ -285,6 +329,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         // ===== epilogue: TMEM -> registers -> ReLU -> Y =====
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        if (tid == 128) KN_STAMP(4);
         const int half = (warp - 4) >> 2;                       // two warps per lane quarter: even / odd 16-column chunks
         const int g_valid = min(Gp, G - row0);
         const int32_t *__restrict__ rg = rows + g * (int64_t)G + row0;
@@ -320,8 +365,11 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
         }
     }
 
+    if (tid == 128) KN_STAMP(5);
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) KN_STAMP(6);
+    if (CS > 1) cluster_sync_all();                              // no CTA leaves while a partner may still signal its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base));
@@ -354,7 +402,7 @@ PFN_encodeTiled get_encode() {
     return fn;
 }
 
-template <int NB, bool DUAL>
+template <int NB, bool DUAL, int CS>
 int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
@@ -372,15 +420,38 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
     KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg_tc: grid too large");
     static bool configured = false;
     if (!configured) {
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    dim3 grid((unsigned)(gx * gy));
-    if (relu) pg_tc_kernel<NB, true, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
-    else      pg_tc_kernel<NB, false, DUAL><<<grid, kThreads, smem, s>>>(maps[0], maps[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b, n_a, a0, X, ldx, Y, ldy, n_vecs);
-    KN_CHECK_LAUNCH();
+    const CUtensorMap *m = maps + (CS > 1 ? 2 : 0);              // maps[2..3]: boxes of Gp/2 rows for the multicast halves
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(gx * gy));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int n_b_ = n_b, n_a_ = n_a;
+    if (relu) KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, true, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs));
+    else      KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, false, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs));
     return KN_OK;
+}
+
+// cluster of 2 along the batch-tile axis whenever the tiles pair up inside a raster super-tile
+template <int NB, bool DUAL>
+int launch_tc_auto(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
+{
+    const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
+    const int64_t n_tiles = kn_cdiv(n_vecs, BM * NB);
+    const int64_t S = kSuperTiles / NB;
+    const bool pairable = (n_tiles % 2 == 0) && (S % 2 == 0) && (Gp % 16 == 0) && ((n_tiles % S) % 2 == 0);
+    if (pairable) return launch_tc<NB, DUAL, 2>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
+    return launch_tc<NB, DUAL, 1>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
 }
 }  // namespace
 
@@ -399,12 +470,12 @@ KN_API int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64
     PFN_encodeTiled enc = get_encode();
     if (!enc) { kn_set_error("cuTensorMapEncodeTiled is not available from this driver"); return KN_ERR_UNSUPPORTED; }
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
-    const float *planes[2] = {vals_hi, vals_lo};
-    for (int i = 0; i < 2; i++) {
+    const float *planes[4] = {vals_hi, vals_lo, vals_hi, vals_lo};
+    for (int i = 0; i < 4; i++) {
         CUtensorMap m;                                         // 64-byte aligned local; the caller's buffer need not be
         cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)n_rows_total};
         cuuint64_t strides[1] = {(cuuint64_t)K_pad * sizeof(float)};
-        cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)Gp};
+        cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)(i < 2 ? Gp : Gp / 2)};   // maps 2,3: half boxes for 2-CTA multicast
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)planes[i], dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -422,17 +493,30 @@ KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const i
     if (n_groups == 0 || n_vecs == 0) return KN_OK;
     KN_REQUIRE(maps_host && rows && cols && X && Y, "spmm_pg_tc: null pointer");
     KN_REQUIRE(n_vecs % 4 == 0 && ldx % 4 == 0 && (((uintptr_t)X) & 15) == 0, "spmm_pg_tc: n_vecs and ldx must be multiples of 4, X 16-byte aligned");
-    KN_REQUIRE(ldx < 0xffffffffLL, "spmm_pg_tc: leading dimension must fit 32 bits");
-    CUtensorMap maps[2];
-    memcpy(maps, maps_host, 2 * sizeof(CUtensorMap));
+    KN_REQUIRE(ldx * 4 < 0xffffffffLL, "spmm_pg_tc: leading dimension in bytes must fit 32 bits");
+    CUtensorMap maps[4];
+    memcpy(maps, maps_host, 4 * sizeof(CUtensorMap));
     const bool relu = (flags & KN_SPMM_RELU) != 0;
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
     // two batch tiles per CTA share every weight stage when accumulators + a >= 2-deep activation ring fit TMEM
-    if (Gp <= 96 && n_vecs > BM)          // 2 tiles x 2*Gp accumulator columns + a 2-deep activation ring fit the 512 TMEM columns
-        return launch_tc<2, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
-    if (Gp <= 128)
-        return launch_tc<1, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    static const int use_dual = getenv("KN_TC_DUAL") ? atoi(getenv("KN_TC_DUAL")) : 1;   // experiment switch
+    if (use_dual && Gp <= 96 && n_vecs > BM)          // 2 tiles x 2*Gp accumulator columns + a 2-deep activation ring fit the 512 TMEM columns
+        return launch_tc_auto<2, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    if (use_dual && Gp <= 128)
+        return launch_tc_auto<1, true>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
     if (2 * Gp + 2 * 64 <= 512 && n_vecs > BM)
-        return launch_tc<2, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
-    return launch_tc<1, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+        return launch_tc_auto<2, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+    return launch_tc_auto<1, false>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, (cudaStream_t)stream);
+}
+
+// debug: select the CTA whose phase timestamps are recorded (-1 = none) / read them back (7 x clock64)
+KN_API int kn_debug_tc_timing(int32_t cta, int64_t *out_host) {
+    if (out_host) {
+        long long t[8];
+        KN_CUDA(cudaMemcpyFromSymbol(t, g_tc_timing, sizeof(t)));
+        for (int i = 0; i < 8; i++) out_host[i] = (int64_t)t[i];
+    }
+    int c = cta;
+    KN_CUDA(cudaMemcpyToSymbol(g_tc_timing_cta, &c, sizeof(int)));
+    return KN_OK;
 }

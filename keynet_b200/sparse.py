@@ -544,7 +544,7 @@ class PatternGroups(object):
                     # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
                     (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
                     check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
-                    maps = ctypes.create_string_buffer(2 * 128)
+                    maps = ctypes.create_string_buffer(4 * 128)
                     check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * int(G), int(G), K_pad, maps))
                     cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
                 pg.classes.append(cls)
