@@ -145,12 +145,17 @@ int kn_linear_fill(const float *weight, const float *bias, int64_t n_out, int64_
  *     dropped if v' == 0                      (scipy SpGEMM drops exact zeros)
  * and writes rows with ascending c' (canonical form).  col_map / row_scale / col_scale may be
  * NULL (identity / 1.0).  No FMA contraction, no flush-to-zero: values are bit-exact with scipy.
+ * row_bias / col_bias (nullable): bias columns of affine photometric keys [[D, b],[0, 1]] (keynet/sparse.py:99-119) on the
+ * left / right: the row's last-column entry becomes fl(a_r*w_last) + row_bias[r] + sum_c fl(fl(a_r*w_c) * col_bias[c]) (a row
+ * reduction: equal to the reference to fp32 rounding; all other entries and all indices stay bit-exact).
  * keep_zeros != 0 keeps exact zeros (the structural matrix the pattern groups are built from, so that a tiny weight
  * rounded to 0 by the reference's offset trick does not split a pixel's rows into different column patterns). */
 int kn_keycompile_count(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                        const float *row_scale, const float *col_scale, int32_t keep_zeros, int64_t *row_nnz, void *stream);
+                        const float *row_scale, const float *col_scale, const float *row_bias, const float *col_bias, int64_t n_cols_in,
+                        int32_t keep_zeros, int64_t *row_nnz, void *stream);
 int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows, int64_t n_cols,
-                       const int32_t *col_map, const float *row_scale, const float *col_scale, int32_t keep_zeros,
+                       const int32_t *col_map, const float *row_scale, const float *col_scale,
+                       const float *row_bias, const float *col_bias, int64_t n_cols_in, int32_t keep_zeros,
                        const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
 
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left

@@ -68,8 +68,8 @@ def lib():
         'kn_toeplitz_conv2d_fill': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, vp],
         'kn_linear_count': [vp, vp, i64, i64, vp, i64, vp, vp],
         'kn_linear_fill': [vp, vp, i64, i64, vp, i64, vp, vp, vp, vp],
-        'kn_keycompile_count': [vp, vp, vp, i64, vp, vp, ctypes.c_int32, vp, vp],
-        'kn_keycompile_fill': [vp, vp, vp, i64, i64, vp, vp, vp, ctypes.c_int32, vp, vp, vp, vp],
+        'kn_keycompile_count': [vp, vp, vp, i64, vp, vp, vp, vp, i64, ctypes.c_int32, vp, vp],
+        'kn_keycompile_fill': [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, ctypes.c_int32, vp, vp, vp, vp],
         'kn_csr_gather_rows_count': [vp, vp, i64, vp, vp],
         'kn_csr_gather_rows_fill': [vp, vp, vp, vp, i64, vp, vp, vp, vp],
         'kn_affine_to_linear_t': [vp, i64, i64, vp, i64, vp],

@@ -51,6 +51,62 @@ keycompile_count_kernel(const int64_t *__restrict__ indptr, const int32_t *__res
     }
 }
 
+// ---- keys with a bias column (affine photometric keys [[D, b],[0, 1]], keynet/sparse.py:99-119) --------------------
+// A = [[diag(a) P, ba],[0, 1]] on the left adds ba[r] to the row's last-column entry (W's last row is e_last);
+// Ainv = [[diag(ai) Pi, bi],[0, 1]] on the right sends every entry t = fl(a_r * w) at column c < last to column
+// col_map[c] with value fl(t * ai[c]) AND adds fl(t * bi[c]) to the last column.  The last-column value of a row is
+// therefore  fl(a_r * w_last) + ba[r] + sum_c fl(t_c * bi[c])  -- a reduction over the row, evaluated by BOTH the
+// count and the fill kernel with this one block-wide routine so they agree bit for bit on whether it is zero.
+// (The summation order differs from scipy's traversal order: the last column matches the reference to fp32
+// rounding, every other entry and all indices stay bit-exact.)
+__device__ __forceinline__ float biased_last_value(const int32_t *__restrict__ indices, const float *__restrict__ data, int64_t beg, int64_t end,
+                                                   int64_t r, int32_t last_in, const float *row_scale, const float *row_bias,
+                                                   const float *col_bias, float *s_red /*[kThreads]*/)
+{
+    float part = 0.0f;
+    for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
+        const int32_t c = indices[e];
+        float t = data[e];
+        if (row_scale) t = __fmul_rn(row_scale[r], t);
+        if (c == last_in) part = __fadd_rn(part, t);
+        else if (col_bias) part = __fadd_rn(part, __fmul_rn(t, col_bias[c]));
+    }
+    s_red[threadIdx.x] = part;
+    __syncthreads();
+    for (int off = kThreads / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) s_red[threadIdx.x] = __fadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + off]);
+        __syncthreads();
+    }
+    float v = s_red[0];
+    __syncthreads();
+    if (row_bias) v = __fadd_rn(v, row_bias[r]);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+keycompile_count_bias_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                             int64_t n_rows, const float *__restrict__ row_scale, const float *__restrict__ col_scale,
+                             const float *__restrict__ row_bias, const float *__restrict__ col_bias, int32_t last_in,
+                             int keep_zeros, int64_t *__restrict__ row_nnz)
+{
+    __shared__ float s_red[kThreads];
+    __shared__ int s_cnt;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int64_t beg = indptr[r], end = indptr[r + 1];
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
+            const int32_t c = indices[e];
+            if (c != last_in) cnt += (keep_zeros || keyed_value(data[e], row_scale, col_scale, r, c) != 0.0f) ? 1 : 0;
+        }
+        if (cnt) atomicAdd(&s_cnt, cnt);
+        const float last = biased_last_value(indices, data, beg, end, r, last_in, row_scale, row_bias, col_bias, s_red);
+        if (threadIdx.x == 0) row_nnz[r] = s_cnt + ((keep_zeros || last != 0.0f) ? 1 : 0);
+        __syncthreads();
+    }
+}
+
 // normalised bitonic sort of n (key,val) pairs by key, ascending; works for any n >= 0
 template <typename KeyPtr, typename ValPtr>
 __device__ __forceinline__ void bitonic_sort_pairs(KeyPtr keys, ValPtr vals, int n) {
@@ -84,19 +140,31 @@ __device__ __forceinline__ void bitonic_sort_pairs(KeyPtr keys, ValPtr vals, int
 __global__ void __launch_bounds__(kThreads)
 keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
                        int64_t n_rows, int64_t n_cols, const int32_t *__restrict__ col_map,
-                       const float *__restrict__ row_scale, const float *__restrict__ col_scale, int keep_zeros,
+                       const float *__restrict__ row_scale, const float *__restrict__ col_scale,
+                       const float *__restrict__ row_bias, const float *__restrict__ col_bias, int32_t last_in, int keep_zeros,
                        const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data)
 {
     extern __shared__ unsigned char smem_raw[];
     int32_t *s_key = reinterpret_cast<int32_t *>(smem_raw);
     float *s_val = reinterpret_cast<float *>(smem_raw + sizeof(int32_t) * kSmemCap);
     __shared__ int s_count;
+    __shared__ float s_red[kThreads];
+    const bool biased = (row_bias != nullptr) || (col_bias != nullptr);   // last_in = old last column, or -1 when no bias is involved
 
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t beg = indptr[r], end = indptr[r + 1];
         const int64_t obeg = out_indptr[r];
-        const int64_t n_out = out_indptr[r + 1] - obeg;
+        int64_t n_out = out_indptr[r + 1] - obeg;
         if (n_out == 0) continue;                               // block-uniform
+        if (biased) {
+            // the last-column entry is a row reduction; it is the largest column, so it goes straight to the row's end
+            const float last = biased_last_value(indices, data, beg, end, r, last_in, row_scale, row_bias, col_bias, s_red);
+            if (keep_zeros || last != 0.0f) {
+                if (threadIdx.x == 0) { out_indices[obeg + n_out - 1] = (int32_t)(n_cols - 1); out_data[obeg + n_out - 1] = last; }
+                n_out -= 1;
+            }
+            if (n_out == 0) continue;
+        }
         const bool in_smem = n_out <= kSmemCap;
         if (!in_smem && n_cols <= kBitmapMaxCols) {
             // ---- long row, moderately wide matrix: rank entries through a column bitmap ----------
@@ -107,6 +175,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
             __syncthreads();
             for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
                 const int32_t c = indices[e];
+                if (biased && c == last_in) continue;
                 if (keep_zeros || keyed_value(data[e], row_scale, col_scale, r, c) != 0.0f) {
                     const int32_t cn = col_map ? col_map[c] : c;
                     atomicOr(&s_bits[cn >> 5], 1u << (cn & 31));
@@ -128,6 +197,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
             __syncthreads();
             for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
                 const int32_t c = indices[e];
+                if (biased && c == last_in) continue;
                 const float v = keyed_value(data[e], row_scale, col_scale, r, c);
                 if (keep_zeros || v != 0.0f) {
                     const int32_t cn = col_map ? col_map[c] : c;
@@ -142,6 +212,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
         __syncthreads();
         for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
             const int32_t c = indices[e];
+            if (biased && c == last_in) continue;
             const float v = keyed_value(data[e], row_scale, col_scale, r, c);
             if (keep_zeros || v != 0.0f) {
                 const int pos = atomicAdd(&s_count, 1);         // order is irrelevant: sorted next
@@ -192,17 +263,26 @@ int row_grid(int64_t n_rows, int rows_per_cta) {
 }  // namespace
 
 KN_API int kn_keycompile_count(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
-                               const float *row_scale, const float *col_scale, int32_t keep_zeros, int64_t *row_nnz, void *stream) {
+                               const float *row_scale, const float *col_scale, const float *row_bias, const float *col_bias, int64_t n_cols_in,
+                               int32_t keep_zeros, int64_t *row_nnz, void *stream) {
     KN_REQUIRE(n_rows >= 0, "keycompile: negative row count");
     if (n_rows == 0) return KN_OK;
     KN_REQUIRE(indptr && indices && data && row_nnz, "keycompile: null pointer");
+    if (row_bias || col_bias) {
+        KN_REQUIRE(n_cols_in > 0, "keycompile: bias keys need the input column count");
+        keycompile_count_bias_kernel<<<row_grid(n_rows, 1), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, row_scale, col_scale,
+                                                                                             row_bias, col_bias, (int32_t)(n_cols_in - 1), keep_zeros, row_nnz);
+        KN_CHECK_LAUNCH();
+        return KN_OK;
+    }
     keycompile_count_kernel<<<row_grid(n_rows, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, row_scale, col_scale, keep_zeros, row_nnz);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
 
 KN_API int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows, int64_t n_cols,
-                              const int32_t *col_map, const float *row_scale, const float *col_scale, int32_t keep_zeros,
+                              const int32_t *col_map, const float *row_scale, const float *col_scale,
+                              const float *row_bias, const float *col_bias, int64_t n_cols_in, int32_t keep_zeros,
                               const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream) {
     KN_REQUIRE(n_rows >= 0, "keycompile: negative row count");
     if (n_rows == 0) return KN_OK;
@@ -214,7 +294,8 @@ KN_API int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, con
         KN_CUDA(cudaFuncSetAttribute(keycompile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    keycompile_fill_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, n_cols, col_map, row_scale, col_scale, keep_zeros,
+    keycompile_fill_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, n_cols, col_map, row_scale, col_scale, row_bias, col_bias,
+                                                                                         (row_bias || col_bias) ? (int32_t)(n_cols_in - 1) : -1, keep_zeros,
                                                                                          out_indptr, out_indices, out_data);
     KN_CHECK_LAUNCH();
     return KN_OK;

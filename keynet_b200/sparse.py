@@ -33,14 +33,25 @@ class MonomialKey(object):
     Covers the reference's identity / permutation / hierarchical block permutation / memory-order
     / diagonal gain keys and all their products (keynet/sparse.py:53-84,272-285,318-321)."""
 
-    def __init__(self, perm, scale=None):
+    def __init__(self, perm, scale=None, bias=None):
+        """bias (optional, homogeneous keys only): extra entries A[r, n-1] = bias[r] for r < n-1 -- the affine
+        photometric keys [[D, b],[0, 1]] (keynet/sparse.py:99-119).  Keys with a bias column are closed under
+        products, so the whole photometric key family stays O(n) on the host."""
         self.perm = np.ascontiguousarray(perm, dtype=np.int64)
         n = len(self.perm)
         self.scale = np.ones(n, dtype=np.float32) if scale is None else np.ascontiguousarray(scale, dtype=np.float32)
         assert self.scale.shape == (n,)
+        self.bias = None
+        if bias is not None:
+            b = np.ascontiguousarray(bias, dtype=np.float32).reshape(-1)
+            assert b.shape == (n,) and b[-1] == 0 and self.perm[-1] == n - 1, 'bias needs a homogeneous key (last row e_last)'
+            self.bias = b
         self.shape = (n, n)
         self.dtype = np.float32
         self.ndim = 2
+
+    def has_bias(self):
+        return self.bias is not None
 
     def __repr__(self):
         return '<keynet_b200.MonomialKey: n=%d, permuted=%s, scaled=%s>' % (self.shape[0], not self.is_unpermuted(), not self.is_unscaled())
@@ -53,7 +64,7 @@ class MonomialKey(object):
         return bool(np.all(self.scale == np.float32(1.0)))
 
     def is_identity(self):
-        return self.is_unpermuted() and self.is_unscaled()
+        return self.is_unpermuted() and self.is_unscaled() and self.bias is None
 
     @property
     def nnz(self):
@@ -64,12 +75,20 @@ class MonomialKey(object):
         """self . other.  other: MonomialKey -> MonomialKey; SparseMatrix -> SparseMatrix (row gather + scale)."""
         if isinstance(other, MonomialKey):
             assert self.shape[1] == other.shape[0], 'non-conformal keys %s, %s' % (str(self.shape), str(other.shape))
-            return MonomialKey(other.perm[self.perm], (self.scale * other.scale[self.perm]).astype(np.float32))
+            bias = None
+            if self.bias is not None or other.bias is not None:
+                # row r of the product: scale_a[r] * (row perm_a[r] of B) + bias_a[r] * e_last; scipy accumulates the
+                # last column as fl(fl(scale_a * bias_b[perm_a]) + bias_a)
+                bb = np.zeros(len(self.perm), dtype=np.float32) if other.bias is None else (self.scale * other.bias[self.perm]).astype(np.float32)
+                bias = bb if self.bias is None else (bb + self.bias).astype(np.float32)
+                bias[-1] = 0
+            return MonomialKey(other.perm[self.perm], (self.scale * other.scale[self.perm]).astype(np.float32), bias)
         if isinstance(other, SparseMatrix):
             return other._left_monomial(self)
         raise TypeError('cannot multiply MonomialKey with %s' % str(type(other)))
 
     def transpose(self):
+        assert self.bias is None, 'a key with a bias column has no monomial transpose (use the inverse from the generator)'
         n = len(self.perm)
         (perm, scale) = (np.empty(n, dtype=np.int64), np.empty(n, dtype=np.float32))
         perm[self.perm] = np.arange(n)
@@ -94,12 +113,18 @@ class MonomialKey(object):
     def todense(self):
         D = np.zeros(self.shape, dtype=np.float32)
         D[np.arange(len(self.perm)), self.perm] = self.scale
+        if self.bias is not None:
+            D[:-1, -1] += self.bias[:-1]
         return D
 
     def toscipy(self, format='csr'):
         import scipy.sparse
         n = len(self.perm)
-        return scipy.sparse.csr_matrix((self.scale, self.perm.astype(np.int32), np.arange(n + 1)), shape=self.shape).asformat(format)
+        A = scipy.sparse.csr_matrix((self.scale, self.perm.astype(np.int32), np.arange(n + 1)), shape=self.shape)
+        if self.bias is not None:
+            nz = np.nonzero(self.bias)[0]
+            A = A + scipy.sparse.csr_matrix((self.bias[nz], (nz, np.full(len(nz), n - 1))), shape=self.shape)
+        return A.asformat(format)
 
 
 def is_key(A):
@@ -161,10 +186,31 @@ def sparse_affine_to_linear(A, bias=None, dtype=np.float32):
     """[A 0; 0 1]: homogeneous augmentation of a key (keynet/sparse.py:87-96).  Keys with a bias
     column are not monomial and belong to the general-key path."""
     assert isinstance(A, MonomialKey), 'sparse_affine_to_linear expects a key matrix'
-    if bias is not None:
-        raise NotImplementedError('affine (bias) keys are not monomial: general key compile is a later scope row')
     n = A.shape[0]
-    return MonomialKey(np.concatenate([A.perm, [n]]), np.concatenate([A.scale, np.ones(1, dtype=np.float32)]))
+    b = None
+    if bias is not None:
+        bias = np.asarray(bias).reshape(-1)
+        assert bias.shape[0] == n
+        b = np.concatenate([bias.astype(np.float32), np.zeros(1, dtype=np.float32)])
+    return MonomialKey(np.concatenate([A.perm, [n]]), np.concatenate([A.scale, np.ones(1, dtype=np.float32)]), b)
+
+
+def diagonal_affine_to_linear(A, bias=None, withinverse=False, dtype=np.float32):
+    """[[D, b],[0, 1]] for a diagonal key D and its inverse [[D^-1, -D^-1 b],[0, 1]] (keynet/sparse.py:99-119).
+    The reference evaluates the inverse with a rank-one (Woodbury) update in float64 and rounds to float32 at the end:
+    diagonal f32(1/d), last column f32(-((1/d)*b)) with d = f64(f32 diagonal), b = the float64 bias."""
+    assert isinstance(A, MonomialKey) and A.is_unpermuted() and A.bias is None, 'diagonal_affine_to_linear expects a diagonal key'
+    n = A.shape[0]
+    L = sparse_affine_to_linear(A, bias)
+    if not withinverse:
+        return L
+    d = A.scale.astype(np.float64)
+    inv = 1.0 / d
+    if bias is None:
+        return (L, MonomialKey(np.arange(n + 1), np.concatenate([inv, [1.0]]).astype(np.float32)))
+    b = np.asarray(bias, dtype=np.float64).reshape(-1)
+    binv = 0.0 - (inv * b * 2.0) / 2.0          # (Ainv u)(v Ainv) / (1 + v Ainv u): the factors of two are exact
+    return (L, MonomialKey(np.arange(n + 1), np.concatenate([inv, [1.0]]).astype(np.float32), np.concatenate([binv, [0.0]]).astype(np.float32)))
 
 
 def sparse_block_diagonal_repeat(B, shape):
@@ -226,12 +272,25 @@ class SparseMatrix(object):
         dev = device if device is not None else _device()
         if isinstance(A, SparseMatrix):
             (self.shape, self._indptr, self._indices, self._data) = (A.shape, A._indptr, A._indices, A._data)
-        elif isinstance(A, MonomialKey):
+        elif isinstance(A, MonomialKey) and A.bias is None:
             n = A.shape[0]
             self.shape = A.shape
             self._indptr = torch.arange(n + 1, dtype=torch.int64, device=dev)
             self._indices = torch.from_numpy(A.perm.astype(np.int32)).to(dev)
             self._data = torch.from_numpy(A.scale).to(dev)
+        elif isinstance(A, MonomialKey):
+            # key with a bias column: one or two entries per row, canonical order (the permuted column is < n-1)
+            n = A.shape[0]
+            has = A.bias != 0
+            counts = 1 + has.astype(np.int64)
+            indptr = np.concatenate([[0], np.cumsum(counts)])
+            indices = np.empty(indptr[-1], dtype=np.int32); data = np.empty(indptr[-1], dtype=np.float32)
+            indices[indptr[:-1]] = A.perm; data[indptr[:-1]] = A.scale
+            indices[indptr[:-1][has] + 1] = n - 1; data[indptr[:-1][has] + 1] = A.bias[has]
+            self.shape = A.shape
+            self._indptr = torch.from_numpy(indptr.astype(np.int64)).to(dev)
+            self._indices = torch.from_numpy(indices).to(dev)
+            self._data = torch.from_numpy(data).to(dev)
         elif isinstance(A, tuple) and len(A) == 4:
             (shape, indptr, indices, data) = A
             self.shape = (int(shape[0]), int(shape[1]))
@@ -641,7 +700,12 @@ def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None, keep_ze
     if A is not None and not A.is_unscaled():
         rs = A.scale if row_scale_slice is None else A.scale[row_scale_slice]
         row_scale = torch.from_numpy(np.ascontiguousarray(rs)).to(dev)
-    (col_map, col_scale) = (None, None)
+    (col_map, col_scale, row_bias, col_bias) = (None, None, None, None)
+    if A is not None and A.bias is not None:
+        rb = A.bias if row_scale_slice is None else A.bias[row_scale_slice]
+        row_bias = torch.from_numpy(np.ascontiguousarray(rb)).to(dev)
+    if Ainv is not None and Ainv.bias is not None:
+        col_bias = torch.from_numpy(Ainv.bias).to(dev)
     n_cols_out = n_cols if Ainv is None else int(Ainv.shape[1])      # physical column space of the compiled matrix
     if Ainv is not None:
         assert Ainv.shape[0] == n_cols
@@ -651,8 +715,8 @@ def _keycompile(csr, n_rows, n_cols, A, Ainv, dev, row_scale_slice=None, keep_ze
             col_scale = torch.from_numpy(Ainv.scale).to(dev)
     return _two_phase(
         n_rows,
-        lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), int(keep_zeros), ptr(row_nnz), stream_ptr())),
-        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols_out, ptr(col_map), ptr(row_scale), ptr(col_scale), int(keep_zeros),
+        lambda row_nnz: check(L.kn_keycompile_count(ptr(indptr), ptr(indices), ptr(data), n_rows, ptr(row_scale), ptr(col_scale), ptr(row_bias), ptr(col_bias), n_cols, int(keep_zeros), ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_keycompile_fill(ptr(indptr), ptr(indices), ptr(data), n_rows, n_cols_out, ptr(col_map), ptr(row_scale), ptr(col_scale), ptr(row_bias), ptr(col_bias), n_cols, int(keep_zeros),
                                                       ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
         dev)
 

@@ -17,7 +17,7 @@ from . import torch as _ktorch
 from . import util as _util
 from .blockpermute import hierarchical_block_permutation_matrix
 from .globals import verbose
-from .sparse import (MonomialKey, sparse_permutation_matrix, sparse_identity_matrix, sparse_uniform_random_diagonal_matrix,
+from .sparse import (MonomialKey, diagonal_affine_to_linear, sparse_permutation_matrix, sparse_identity_matrix, sparse_uniform_random_diagonal_matrix,
                      sparse_channelorder_to_blockorder_matrix, sparse_channelorder_to_pixelorder_matrix, sparse_affine_to_linear,
                      sparse_block_diagonal_repeat)
 
@@ -274,8 +274,9 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
     """Compose A = C^-1 . p . g . P . G . C and its inverse for one activation shape (keynet/system.py:317-469).
 
     RNG draws happen in the reference's order: global geometric, local geometric, global photometric, local
-    photometric.  Options whose key is not monomial (bias / affine photometric keys, Givens and doubly-stochastic
-    geometric keys) need the general key compile and raise NotImplementedError for now."""
+    photometric.  All photometric options are supported (gain keys are monomial; bias / affine keys are monomial
+    plus a bias column, a family closed under products).  Givens-orthogonal and doubly-stochastic geometric keys need a
+    general sparse key compile and raise NotImplementedError for now."""
     allowable_memoryorder = set(['channel', 'block'])
     allowable_global_geometric = set(['identity', 'permutation', 'hierarchical_permutation', 'hierarchical_rotation', 'givens_orthogonal'])
     allowable_local_geometric = set(['identity', 'permutation', 'doubly_stochastic', 'givens_orthogonal'])
@@ -350,8 +351,22 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
         assert beta is not None and beta > 0
         (P, Pinv) = sparse_uniform_random_diagonal_matrix(N, beta, bias=1, withinverse=True)
         (P, Pinv) = (sparse_affine_to_linear(P), sparse_affine_to_linear(Pinv))
-    elif global_photometric in allowable_photometric:
-        raise NotImplementedError("global_photometric='%s' " % global_photometric + general)
+    elif global_photometric == 'uniform_random_bias':
+        assert gamma is not None and gamma > 0
+        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), gamma * np.random.rand(N, 1), withinverse=True)
+    elif global_photometric == 'linear_bias':
+        assert gamma is not None and gamma > 0
+        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), (gamma / float(N)) * np.array(range(0, N)).reshape(N, 1), withinverse=True)
+    elif global_photometric == 'uniform_random_affine':
+        assert tileshape is None, "Global permutation is not tile compressible"
+        assert beta is not None and beta > 0 and gamma is not None and gamma > 0
+        P = sparse_uniform_random_diagonal_matrix(N, beta, bias=1)
+        (P, Pinv) = diagonal_affine_to_linear(P, gamma * np.random.rand(N, 1), withinverse=True)
+    elif global_photometric == 'blockwise_constant_bias':
+        assert gamma is not None and gamma > 0
+        assert blocksize is not None
+        bias = gamma * np.random.rand(int(np.ceil(N // blocksize)), 1).dot(np.ones((1, blocknumel))).flatten()[0:N].reshape(N, 1)
+        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), bias, withinverse=True)
     else:
         raise ValueError("Invalid global photometric transform '%s' - must be in '%s'" % (global_photometric, str(allowable_photometric)))
 
@@ -363,10 +378,19 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
         (p, pinv) = sparse_uniform_random_diagonal_matrix(blocknumel, beta, bias=1, withinverse=True)
         (p, pinv) = (_repeat_diagonal(p, N), _repeat_diagonal(pinv, N))
         (p, pinv) = (sparse_affine_to_linear(p), sparse_affine_to_linear(pinv))
+    elif local_photometric == 'uniform_random_bias':
+        assert blocksize is not None
+        assert gamma is not None and gamma > 0
+        bias = np.tile(gamma * np.random.rand(blocknumel), int(np.ceil(N / blocknumel)))[0:N].reshape(N, 1)
+        (p, pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), bias=bias, withinverse=True)
+    elif local_photometric == 'uniform_random_affine':
+        assert blocksize is not None
+        assert beta is not None and beta > 0 and gamma is not None and gamma > 0
+        p = sparse_uniform_random_diagonal_matrix(blocknumel, beta, bias=1)
+        bias = np.tile(gamma * np.random.rand(blocknumel), int(np.ceil(N / blocknumel)))[0:N].reshape(N, 1)
+        (p, pinv) = diagonal_affine_to_linear(_repeat_diagonal(p, N), bias=bias, withinverse=True)
     elif local_photometric == 'blockwise_constant_bias':
         raise ValueError('blockwise_constant_bias supported for global_photometric testing only')
-    elif local_photometric in allowable_photometric:
-        raise NotImplementedError("local_photometric='%s' " % local_photometric + general)
     else:
         raise ValueError("Invalid local photometric transform '%s' - must be in '%s'" % (local_photometric, str(allowable_photometric)))
 

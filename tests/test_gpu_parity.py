@@ -563,3 +563,54 @@ def test_save_and_load_compiled_keynet(tmp_path):
     xc = sensor.fromtensor(x).encrypt().astensor()
     (s3, k3) = io.load(io.save(str(tmp_path / 'public.keynet'), None, knet.public()))
     assert s3 is None and np.array_equal(k3.forward(xc).reshape(40, -1).numpy(), y)
+
+
+# ---------------------------------------------------------------------------------------------
+# photometric bias / affine keys (keys with a bias column)
+def test_keycompile_bias_keys_vs_oracle():
+    """A = [[D P, b],[0, 1]] on both sides: indices bit-exact, every value bit-exact except the last column, which is a
+    row reduction (fp32 rounding; scipy sums it in its own traversal order)."""
+    from keynet_b200 import sparse
+    ko = _ko()
+    rs = np.random.RandomState(21)
+    (C, U, V, M) = (3, 6, 8, 5)
+    f = rs.randn(M, C, 3, 3).astype(np.float32); b = rs.randn(M).astype(np.float32)
+    (R, K) = (M * U * V + 1, C * U * V + 1)
+
+    def affine_key(n, permute):
+        perm = np.concatenate([rs.permutation(n - 1), [n - 1]]) if permute else np.arange(n)
+        scale = np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32)
+        bias = np.concatenate([rs.rand(n - 1), [0.0]]).astype(np.float32)
+        return sparse.MonomialKey(perm, scale, bias)
+    for (A, Ainv) in [(affine_key(R, True), affine_key(K, True)), (None, affine_key(K, False)), (affine_key(R, False), sparse.MonomialKey(np.arange(K)))]:
+        W = sparse.keyed_toeplitz_conv2d((C, U, V), f, b, 1, A, Ainv)
+        ref = ko.sort_indices(ko.key_compile(None if A is None else ko.csr_from_dense(A.todense()), ko.toeplitz_conv2d((C, U, V), f, b, 1), ko.csr_from_dense(Ainv.todense())))
+        (ip, ix, dt) = W.csr_arrays()
+        assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices)
+        last = ix == K - 1
+        assert np.array_equal(dt[~last].view(np.uint32), ref.data[~last].view(np.uint32))
+        assert np.allclose(dt[last], ref.data[last], rtol=1e-5, atol=1e-6)
+        assert last.sum() >= R - 1                        # the bias column is dense
+
+
+def test_photometric_keynets_match_plain_net():
+    """reference test/test_keynet.py:65-81: gain / bias / affine global photometric keys, keyed == plain."""
+    from keynet_b200 import system, nets
+    torch.manual_seed(7)
+    net = nets.LeNet_AvgPool().eval()
+    x = torch.randn(4, 1, 28, 28)
+    yp = net(x).detach().numpy()
+    for (kw, atol) in [(dict(global_photometric='uniform_random_gain', beta=1.0), 1e-5),
+                       (dict(global_photometric='uniform_random_bias', gamma=1.0), 1e-5),
+                       (dict(global_photometric='uniform_random_affine', beta=1.0, gamma=1.0), 1e-4),
+                       (dict(global_geometric='permutation', global_photometric='uniform_random_affine', beta=1.0, gamma=1.0), 1e-4),
+                       (dict(global_photometric='linear_bias', gamma=2.0), 1e-4)]:
+        np.random.seed(1)
+        (sensor, knet) = system.Keynet((1, 28, 28), net, **kw)
+        xc = sensor.fromtensor(x).encrypt().astensor()
+        y = knet.forward(xc).reshape(4, -1).numpy()
+        assert np.allclose(y, yp, atol=atol), (kw, np.abs(y - yp).max())
+        xd = sensor.decrypt().astensor()
+        assert np.allclose(xd.numpy(), x.numpy(), atol=1e-4)
+        if 'bias' in kw['global_photometric'] or 'affine' in kw['global_photometric']:
+            assert not np.allclose(xc.numpy()[:, :-1], x.reshape(4, -1).numpy(), atol=1e-3)      # the image really is keyed

@@ -33,12 +33,28 @@ def test_keygen_matches_reference(name):
 
 
 @pytest.mark.parametrize('name', ['bias', 'affine'])
-def test_keygen_general_keys_are_refused_loudly(name):
+def test_keygen_bias_keys_match_reference(name):
+    """Affine photometric keys [[D P, b],[0, 1]] and their Woodbury inverses: dense forms bit-equal to the reference."""
+    import scipy.sparse
     z = gu.load('keygen_kat.npz')
     kw = gu.jstr(z, name + '.args')
     shape = tuple(kw.pop('shape'))
+    np.random.seed(11)
+    (A, Ainv) = system.keygen(shape, **kw)
+    assert A.has_bias() and Ainv.has_bias()
+    for (K, pre) in ((A, name + '.A'), (Ainv, name + '.Ainv')):
+        (shp, row, col, data) = gu.coo_arrays(z, pre)
+        ref = np.asarray(scipy.sparse.coo_matrix((data, (row, col)), shape=shp).todense(), dtype=np.float32)
+        assert np.array_equal(K.todense().view(np.uint32), ref.view(np.uint32)), pre
+    I = A.dot(Ainv).todense()
+    assert np.allclose(I, np.eye(I.shape[0]), atol=1e-5)
+
+
+def test_keygen_general_geometric_keys_are_refused_loudly():
     with pytest.raises(NotImplementedError):
-        system.keygen(shape, **kw)
+        system.keygen((1, 8, 8), 'givens_orthogonal', 'identity', 'identity', 'identity', alpha=2)
+    with pytest.raises(NotImplementedError):
+        system.keygen((1, 8, 8), 'identity', 'doubly_stochastic', 'identity', 'identity', alpha=2, blocksize=4)
 
 
 def test_keygen_rejects_unknown_options():
