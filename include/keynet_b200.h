@@ -48,6 +48,13 @@ const char *kn_last_error(void);
 /* Device facts used to size grids (returns KN_ERR_CUDA if no device). */
 int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *total_mem_bytes);
 
+/* ---- fused SpMM + all-gather (kernel K5) --------------------------------------------------------------
+ * After kn_output_peers(ptrs, n) every kn_spmm_* call of the calling thread stores each output row to ALL n buffers
+ * (ptrs[i] = address on peer i of the same Y argument; NVLink peer mappings, e.g. torch symmetric memory) instead of
+ * to its Y argument: the row-sharded layer writes its slot of every rank's gathered activation buffer from the
+ * epilogue, so no separate all-gather runs.  n = 0 restores single-destination stores.  HOST array of device pointers. */
+int kn_output_peers(const uint64_t *peer_y_host, int32_t n);
+
 /* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------
  * Replaces SparseMatrix.torchdot (keynet/sparse.py:488-492 -> scipy csr_matvecs), called from
  * KeyedLayer.forward / .decrypt (keynet/layer.py:92,99) and KeyedSensor.encrypt (system.py:254).

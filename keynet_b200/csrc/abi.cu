@@ -38,3 +38,15 @@ KN_API int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *
     if (total_mem_bytes) *total_mem_bytes = (int64_t)p.totalGlobalMem;
     return KN_OK;
 }
+
+static thread_local KnPeers g_peers = {0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+
+KnPeers kn_current_peers() { return g_peers; }
+
+KN_API int kn_output_peers(const uint64_t *peer_y_host, int32_t n) {
+    KN_REQUIRE(n >= 0 && n <= 8, "output_peers: between 0 and 8 peers (got %d)", n);
+    KN_REQUIRE(n == 0 || peer_y_host != nullptr, "output_peers: null pointer list");
+    g_peers.n = n;
+    for (int i = 0; i < 8; i++) g_peers.y[i] = (i < n) ? reinterpret_cast<float *>(peer_y_host[i]) : nullptr;
+    return KN_OK;
+}

@@ -32,6 +32,11 @@ void kn_set_error(const char *fmt, ...);
 
 static inline int64_t kn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Output replication for the fused SpMM + all-gather (K5): when n > 0 every epilogue stores its rows to all n buffers
+// (its own and the peers' NVLink-mapped ones, same layout everywhere) instead of the single Y it was given.
+struct KnPeers { int n; float *y[8]; };
+KnPeers kn_current_peers();     // thread-local list set by kn_output_peers() (abi.cu)
+
 // number of SMs of the current device (cached); B200 = 148
 int kn_sm_count();
 

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
              const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of,
              int G, int Gp, int K_pad, int chunks_per_group, int64_t n_items, int64_t n_tiles, int n_b, int n_a, uint32_t a0,
-             const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs)
+             const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const KnPeers peers)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -357,7 +357,9 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             float y = __uint_as_float(r[t]);
                             if (DUAL) y += __uint_as_float(r2[t]);
                             if (RELU) y = fmaxf(y, 0.0f);
-                            Y[(int64_t)__ldg(rg + c0 + t) * ldy + ne] = y;
+                            const int64_t yoff = (int64_t)__ldg(rg + c0 + t) * ldy + ne;
+                            if (peers.n == 0) Y[yoff] = y;
+                            else for (int p = 0; p < peers.n; p++) peers.y[p][yoff] = y;     // fused all-gather over NVLink peer memory
                         }
                     }
                 }
@@ -436,8 +438,9 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int n_b_ = n_b, n_a_ = n_a;
-    if (relu) KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, true, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs));
-    else      KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, false, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs));
+    const KnPeers peers = kn_current_peers();
+    if (relu) KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, true, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs, peers));
+    else      KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, false, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs, peers));
     return KN_OK;
 }
 

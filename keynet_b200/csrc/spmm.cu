@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                     const float *__restrict__ data, int64_t n_rows,
                     const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs,
-                    const int32_t *__restrict__ out_rows)
+                    const int32_t *__restrict__ out_rows, const KnPeers peers)
 {
     __shared__ int2 s_ent[kWarps][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,10 +101,14 @@ spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
 #pragma unroll
             for (int i = 0; i < V; i++) acc[i] = fmaxf(acc[i], 0.0f);
         }
-        float *yp = Y + (out_rows ? (int64_t)out_rows[row] : row) * ldy + n0;
-        if constexpr (V == 4) *reinterpret_cast<float4 *>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        else if constexpr (V == 2) *reinterpret_cast<float2 *>(yp) = make_float2(acc[0], acc[1]);
-        else yp[0] = acc[0];
+        const int64_t yoff = (out_rows ? (int64_t)out_rows[row] : row) * ldy + n0;
+        const int np = peers.n > 0 ? peers.n : 1;
+        for (int p = 0; p < np; p++) {                           // fused all-gather: the row goes to every peer's buffer
+            float *yp = (peers.n > 0 ? peers.y[p] : Y) + yoff;
+            if constexpr (V == 4) *reinterpret_cast<float4 *>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            else if constexpr (V == 2) *reinterpret_cast<float2 *>(yp) = make_float2(acc[0], acc[1]);
+            else yp[0] = acc[0];
+        }
     }
 }
 
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                       const float *__restrict__ data, int64_t n_rows,
                       const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int n_vecs,
-                      const int32_t *__restrict__ out_rows)
+                      const int32_t *__restrict__ out_rows, const KnPeers peers)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
@@ -138,7 +142,11 @@ spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restr
     }
 #pragma unroll
     for (int n = 0; n < NB; n++)
-        if (lane == n && n < n_vecs) Y[yrow * ldy + n] = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
+        if (lane == n && n < n_vecs) {
+            const float o = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
+            const int np = peers.n > 0 ? peers.n : 1;
+            for (int p = 0; p < np; p++) (peers.n > 0 ? peers.y[p] : Y)[yrow * ldy + n] = o;
+        }
 }
 
 template <int V>
@@ -148,8 +156,8 @@ int launch_rowwarp(const int64_t *indptr, const int32_t *indices, const float *d
     const int64_t gx = kn_cdiv(n_rows, kWarps), gy = kn_cdiv(n_vecs, 32 * V);
     KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large (rows=%lld, n_vecs=%lld)", (long long)n_rows, (long long)n_vecs);
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (relu) spmm_rowwarp_kernel<V, true><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
-    else      spmm_rowwarp_kernel<V, false><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
+    if (relu) spmm_rowwarp_kernel<V, true><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
+    else      spmm_rowwarp_kernel<V, false><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -160,8 +168,8 @@ int launch_lanes(const int64_t *indptr, const int32_t *indices, const float *dat
 {
     const int64_t gx = kn_cdiv(n_rows, kWarps);
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm: too many rows (%lld)", (long long)n_rows);
-    if (relu) spmm_lanes_nnz_kernel<NB, true><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
-    else      spmm_lanes_nnz_kernel<NB, false><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows);
+    if (relu) spmm_lanes_nnz_kernel<NB, true><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
+    else      spmm_lanes_nnz_kernel<NB, false><<<(unsigned)gx, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
     KN_CHECK_LAUNCH();
     return KN_OK;
 }

@@ -77,9 +77,14 @@ class ShardedLayerGen(object):
 class ShardedKeyedModel(object):
     """Row-sharded keyed network: same constructor contract as system.Keynet(...)[1] plus (rank, world, group)."""
 
-    def __init__(self, inshape, net, rank, world, group=None, **keynet_kwargs):
+    def __init__(self, inshape, net, rank, world, group=None, fused=False, **keynet_kwargs):
+        """fused=True: no NCCL on the data path -- every SpMM epilogue stores its rows straight into all ranks' gathered
+        activation buffers (torch symmetric memory = NVLink peer mappings, kn_output_peers), one device-side barrier per
+        layer.  fused=False: local SpMM + torch.distributed all_gather_into_tensor (NCCL)."""
         from . import system
         self.rank, self.world, self.group = int(rank), int(world), group
+        self.fused = bool(fused) and self.world > 1
+        self._symm = {}
         f_keypair = system.keypair_policy(**keynet_kwargs)
         self.sensor = system.KeyedSensor(inshape, f_keypair('input', inshape))
         self._gen = ShardedLayerGen(rank, world, inshape)
@@ -90,6 +95,43 @@ class ShardedKeyedModel(object):
     def num_parameters_local(self):
         return sum(L.nnz() for L in self.layers)
 
+    def _symm_buffers(self, N, dev):
+        """Two ping-pong symmetric buffers (layer k writes buffer k%2 on every rank while buffer (k-1)%2 is being read)."""
+        if N not in self._symm:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            rows = max(L._shard.n_phys for L in self.layers)
+            bufs = []
+            for _ in range(2):
+                t = symm_mem.empty((rows * N,), dtype=torch.float32, device=dev)
+                h = symm_mem.rendezvous(t, group)
+                bufs.append((t, h))
+            self._symm[N] = bufs
+        return self._symm[N]
+
+    def _forward_fused(self, X, N, dev):
+        from . import _native
+        from .sparse import spmm
+        bufs = self._symm_buffers(N, dev)
+        for (k, L) in enumerate(self.layers):
+            sh = L._shard
+            relu = L._fused_relu or ('ReLU' in L._layertype)
+            (t, h) = bufs[k % 2]
+            Yfull = t[:sh.n_phys * N].view(sh.n_phys, N)
+            n_mine = len(sh.my_rows)
+            slot = self.rank * sh.chunk * N * 4                         # byte offset of this rank's slot in every buffer
+            if n_mine > 0:
+                _native.set_output_peers([int(p) + slot for p in h.buffer_ptrs])
+                try:
+                    spmm(L.W, X, relu=relu, out=Yfull[self.rank * sh.chunk:self.rank * sh.chunk + n_mine])
+                finally:
+                    _native.set_output_peers([])
+            Yfull[-1].fill_(1.0)                                        # homogeneous coordinate: local
+            h.barrier()                                                 # every rank's stores have landed everywhere
+            X = Yfull
+        return X
+
     def forward_linear(self, x_cipher):
         """x_cipher: N x (D+1) encrypted batch, identical on every rank.  Returns N x (K+1) on every rank."""
         import torch.distributed as dist
@@ -97,6 +139,10 @@ class ShardedKeyedModel(object):
         dev = torch.device('cuda', torch.cuda.current_device())
         X = x_cipher.to(dev).t().contiguous()                         # feature-major [D+1, N]
         N = X.shape[1]
+        if self.fused:
+            X = self._forward_fused(X, N, dev)
+            pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
+            return X[pos].t().contiguous()
         for L in self.layers:
             sh = L._shard
             relu = L._fused_relu or ('ReLU' in L._layertype)
