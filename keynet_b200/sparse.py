@@ -510,7 +510,8 @@ def _dedup_value_blocks(cols, vals, group_k, ng, G, K_pad, chunk_bytes=1 << 30):
             ok = False
             break
     if not ok:
-        warnings.warn('value-block hash collision: blocks of this class are stored per group')
+        nbad = int(sum(int((v3[g0:min(ng, g0 + step)].view(torch.int32) != v3[rep[g0:min(ng, g0 + step)]].view(torch.int32)).flatten(1).any(dim=1).sum()) for g0 in range(0, ng, step)))
+        warnings.warn('value-block hash collision: blocks of this class are stored per group (G=%d K_pad=%d groups=%d unique hashes=%d mismatching groups=%d)' % (G, K_pad, ng, nu, nbad))
         return (cols, vals, None)
     vals_u = v3[first].contiguous().view(-1)
     return (cols, vals_u, inverse.to(torch.int32).contiguous())

@@ -26,3 +26,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _built_library():
+    """Make sure libkeynet_b200.so and the C oracle exist (no-ops when they are up to date; nvcc / gcc cross-compile
+    without a GPU).  Building the checker is not using it."""
+    try:
+        from keynet_b200 import build as kb
+        kb.build()
+        from oracle import keynet_oracle
+        keynet_oracle.build()
+    except Exception as e:          # report, but let the tests that need the library fail loudly on their own
+        print('[conftest] build failed: %s' % e)
+    yield
