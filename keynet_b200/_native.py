@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libkeynet_b200.so')
+LIB_PATH = os.environ.get('KEYNET_B200_LIB', os.path.join(_HERE, 'lib', 'libkeynet_b200.so'))
 
 KN_SPMM_RELU = 1
 

@@ -35,6 +35,11 @@ static inline int64_t kn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // Output replication for the fused SpMM + all-gather (K5): when n > 0 every epilogue stores its rows to all n buffers
 // (its own and the peers' NVLink-mapped ones, same layout everywhere) instead of the single Y it was given.
 struct KnPeers { int n; float *y[8]; };
+// Kernels take it as `const __grid_constant__ KnPeers`, so the pointer list is read straight from the constant bank
+// (a plain by-value struct indexed at run time would be copied to local memory and slow every epilogue).
+#define KN_FOR_EACH_DEST(peers, Y, dst)                                                       \
+    for (int p_ = 0, np_ = ((peers).n > 0 ? (peers).n : 1); p_ < np_; p_++)                   \
+        if (float *dst = ((peers).n > 0 ? (peers).y[p_] : (Y)); true)
 KnPeers kn_current_peers();     // thread-local list set by kn_output_peers() (abi.cu)
 
 // number of SMs of the current device (cached); B200 = 148

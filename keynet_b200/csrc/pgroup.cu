@@ -103,7 +103,7 @@ template <int RW, bool RELU>
 __global__ void __launch_bounds__(kThreads, 2)
 pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
                const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_groups, int G, int K_pad, int tiles_per_group, int64_t n_items, int64_t n_tiles,
-               const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const KnPeers peers)
+               const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     constexpr int TM = 8 * RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -191,8 +191,8 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
                 const int64_t yrow = rows[g * G + (int64_t)rowtile * TM + r];
                 float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
                 if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
-                const int np = peers.n > 0 ? peers.n : 1;
-                for (int p = 0; p < np; p++) *reinterpret_cast<float4 *>((peers.n > 0 ? peers.y[p] : Y) + yrow * ldy + n0) = o;
+                if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yrow * ldy + n0) = o;
+                else KN_FOR_EACH_DEST(peers, Y, yb) *reinterpret_cast<float4 *>(yb + yrow * ldy + n0) = o;
             }
         }
     }
@@ -206,7 +206,7 @@ template <int GM, bool RELU>
 __global__ void __launch_bounds__(kThreads)
 pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
                 const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_groups, int G, int K_pad, int64_t n_supers, int tiles_per_super,
-                const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const KnPeers peers)
+                const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,8 +253,8 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
                     float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                     const int64_t yoff = (int64_t)__ldg(rows + g * G + r) * ldy + n0;
-                    const int np = peers.n > 0 ? peers.n : 1;
-                    for (int p = 0; p < np; p++) *reinterpret_cast<float4 *>((peers.n > 0 ? peers.y[p] : Y) + yoff) = o;
+                    if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yoff) = o;
+                    else KN_FOR_EACH_DEST(peers, Y, yb) *reinterpret_cast<float4 *>(yb + yoff) = o;
                 }
             }
         }

@@ -35,7 +35,7 @@ constexpr int kThreads = 384;          // warp 0: TMA(B)  warps 1,3: MMA issuers
 constexpr int kProducerThreads = 256;
 constexpr int KS = 16;                 // k per stage
 constexpr int BM = 128;                // batch columns per UMMA (M)
-constexpr int kSuperTiles = 16;        // rasterisation super-tile: 16 x 128 = 2048 batch columns
+constexpr int kSuperTiles = 8;         // rasterisation super-tile: 8 x 128 = 1024 batch columns (sweep 4..32: 4/8 best by ~1 %)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -138,12 +138,12 @@ __device__ long long g_tc_timing[8];
 __device__ int g_tc_timing_cta = -1;
 #define KN_STAMP(i) do { if ((int)blockIdx.x == g_tc_timing_cta) g_tc_timing[i] = clock64(); } while (0)
 
-template <int NB, bool RELU, bool DUAL, int CS>
+template <int NB, bool RELU, bool DUAL, int CS, bool PEERS>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
              const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of,
-             int G, int Gp, int K_pad, int chunks_per_group, int64_t n_items, int64_t n_tiles, int n_b, int n_a, uint32_t a0,
-             const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const KnPeers peers)
+             int G, int Gp, int K_pad, int chunks_per_group, int64_t n_items, int64_t n_tiles, int n_b, int n_a, uint32_t a0, int super_tiles,
+             const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -158,7 +158,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const KnRaster rt = kn_raster(blockIdx.x, n_items, n_tiles, kSuperTiles / NB);
+    const KnRaster rt = kn_raster(blockIdx.x, n_items, n_tiles, super_tiles);
     const int64_t g = rt.item / chunks_per_group;                // pattern group
     const int gchunk = (int)(rt.item - g * chunks_per_group);    // 256-row chunk of a very tall group
     const int row0 = gchunk * 256;                               // first group row handled here
@@ -358,8 +358,8 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                             if (DUAL) y += __uint_as_float(r2[t]);
                             if (RELU) y = fmaxf(y, 0.0f);
                             const int64_t yoff = (int64_t)__ldg(rg + c0 + t) * ldy + ne;
-                            if (peers.n == 0) Y[yoff] = y;
-                            else for (int p = 0; p < peers.n; p++) peers.y[p][yoff] = y;     // fused all-gather over NVLink peer memory
+                            if constexpr (!PEERS) Y[yoff] = y;                                  // (separate instantiation: the peer loop
+                            else KN_FOR_EACH_DEST(peers, Y, yb) yb[yoff] = y;                   //  costs the plain epilogue ~10 %) NVLink peer stores
                         }
                     }
                 }
@@ -404,6 +404,13 @@ PFN_encodeTiled get_encode() {
     return fn;
 }
 
+// batch columns (in 128-column tiles) per raster super-tile: small enough that the X rows shared by neighbouring groups
+// (3x3 windows re-read every row 9 times, one image row of groups apart) are still L2-resident when they are re-read
+static int tc_super_tiles() {
+    static const int v = getenv("KN_TC_SUPER") ? atoi(getenv("KN_TC_SUPER")) : kSuperTiles;
+    return v > 0 ? v : kSuperTiles;
+}
+
 template <int NB, bool DUAL, int CS>
 int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
@@ -422,8 +429,10 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
     KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg_tc: grid too large");
     static bool configured = false;
     if (!configured) {
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     const CUtensorMap *m = maps + (CS > 1 ? 2 : 0);              // maps[2..3]: boxes of Gp/2 rows for the multicast halves
@@ -438,9 +447,13 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int n_b_ = n_b, n_a_ = n_a;
+    const int super_ = tc_super_tiles() / NB > 0 ? tc_super_tiles() / NB : 1;
     const KnPeers peers = kn_current_peers();
-    if (relu) KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, true, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs, peers));
-    else      KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, false, DUAL, CS>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, chunks_per_group, gx, gy, n_b_, n_a_, a0, X, ldx, Y, ldy, n_vecs, peers));
+#define KN_TC_LAUNCH(R, P) KN_CUDA(cudaLaunchKernelEx(&cfg, pg_tc_kernel<NB, R, DUAL, CS, P>, m[0], m[1], rows, cols, group_k, block_of, G, Gp, K_pad, \
+                                                     chunks_per_group, gx, gy, n_b_, n_a_, a0, super_, X, ldx, Y, ldy, n_vecs, peers))
+    if (peers.n > 0) { if (relu) KN_TC_LAUNCH(true, true); else KN_TC_LAUNCH(false, true); }
+    else             { if (relu) KN_TC_LAUNCH(true, false); else KN_TC_LAUNCH(false, false); }
+#undef KN_TC_LAUNCH
     return KN_OK;
 }
 
@@ -451,7 +464,7 @@ int launch_tc_auto(const CUtensorMap *maps, const int32_t *rows, const int32_t *
 {
     const int Gp = (G > 256) ? 256 : ((G + 15) / 16) * 16;
     const int64_t n_tiles = kn_cdiv(n_vecs, BM * NB);
-    const int64_t S = kSuperTiles / NB;
+    const int64_t S = tc_super_tiles() / NB > 0 ? tc_super_tiles() / NB : 1;
     const bool pairable = (n_tiles % 2 == 0) && (S % 2 == 0) && (Gp % 16 == 0) && ((n_tiles % S) % 2 == 0);
     if (pairable) return launch_tc<NB, DUAL, 2>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);
     return launch_tc<NB, DUAL, 1>(maps, rows, cols, group_k, block_of, n_groups, G, K_pad, X, ldx, Y, ldy, n_vecs, relu, s);

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                     const float *__restrict__ data, int64_t n_rows,
                     const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs,
-                    const int32_t *__restrict__ out_rows, const KnPeers peers)
+                    const int32_t *__restrict__ out_rows, const __grid_constant__ KnPeers peers)
 {
     __shared__ int2 s_ent[kWarps][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,9 +102,8 @@ spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
             for (int i = 0; i < V; i++) acc[i] = fmaxf(acc[i], 0.0f);
         }
         const int64_t yoff = (out_rows ? (int64_t)out_rows[row] : row) * ldy + n0;
-        const int np = peers.n > 0 ? peers.n : 1;
-        for (int p = 0; p < np; p++) {                           // fused all-gather: the row goes to every peer's buffer
-            float *yp = (peers.n > 0 ? peers.y[p] : Y) + yoff;
+        KN_FOR_EACH_DEST(peers, Y, yb) {                         // fused all-gather: the row goes to every peer's buffer
+            float *yp = yb + yoff;
             if constexpr (V == 4) *reinterpret_cast<float4 *>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             else if constexpr (V == 2) *reinterpret_cast<float2 *>(yp) = make_float2(acc[0], acc[1]);
             else yp[0] = acc[0];
@@ -117,7 +116,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                       const float *__restrict__ data, int64_t n_rows,
                       const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int n_vecs,
-                      const int32_t *__restrict__ out_rows, const KnPeers peers)
+                      const int32_t *__restrict__ out_rows, const __grid_constant__ KnPeers peers)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
@@ -144,8 +143,7 @@ spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restr
     for (int n = 0; n < NB; n++)
         if (lane == n && n < n_vecs) {
             const float o = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
-            const int np = peers.n > 0 ? peers.n : 1;
-            for (int p = 0; p < np; p++) (peers.n > 0 ? peers.y[p] : Y)[yrow * ldy + n] = o;
+            KN_FOR_EACH_DEST(peers, Y, yb) yb[yrow * ldy + n] = o;
         }
 }
 
