@@ -238,6 +238,78 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
+def run_row_sharded(args, rank, world, local_rank):
+    """Strong scaling: ONE batch, every keyed layer's rows cut into `world` shards (keynet_b200/dist.py), activations
+    all-gathered per layer over NVLink (NCCL, or fused into the SpMM epilogue with --parallel rows-fused)."""
+    import torch
+    import torch.distributed as dist
+    from keynet_b200 import dist as kdist
+    wl = workload(args.net)
+    keys = {k: v for (k, v) in wl['keys'].items() if k != 'keep_csr'}
+    N = args.batch
+    t0 = time.perf_counter()
+    np.random.seed(0)
+    m = kdist.ShardedKeyedModel(wl['inshape'], wl['net'], rank=rank, world=world, fused=(args.parallel == 'rows-fused'), keep_csr=False, **keys)
+    torch.cuda.synchronize()
+    t_compile = time.perf_counter() - t0
+    x = torch.randn((N,) + wl['inshape'], generator=torch.Generator().manual_seed(1)).cuda()      # same batch on every rank
+    K = args.steps
+
+    def step():
+        return m.forward_linear(m.sensor.fromtensor(x).encrypt().astensor())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        y = step()
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    (e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e0.record()
+    for _ in range(K):
+        y = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+    layer_ms = None
+    if True:                                      # one extra (untimed) forward with per-layer events
+        m.time_layers = True
+        step()
+        layer_ms = [(type(m._model).__name__ and k, round(a, 3), round(b, 3)) for (k, a, b) in m.layer_times_ms()]
+        m.time_layers = False
+    nnz_local = m.num_parameters_local()
+    stats = torch.tensor([ms, float(nnz_local), torch.cuda.max_memory_allocated() / 1e9], device='cuda', dtype=torch.float64)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        (mx, sm) = (stats, stats)
+    ms = float(mx[0])
+    if rank == 0:
+        (peak, peak_src) = hbm_peak()
+        nnz = float(sm[1])
+        act = sum((L.W.shape[0] * 0 + L._shard.n_rows + L.W.shape[1]) * N * 4 for L in m.layers)          # every rank reads X_full; rows written once
+        alg = nnz * 8 + act
+        gather = sum((L._shard.n_phys - 1) * N * 4 for L in m.layers)
+        hbm = alg / (ms / K * 1e-3) / 1e9
+        out = {'metric': 'encrypted_images_per_sec', 'value': N * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': args.warmup,
+               'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': wl['label'], 'global_batch': N, 'parallelism': 'rows x%d, %s' % (world, 'fused SpMM+all-gather (NVLink peer stores)' if m.fused else 'NCCL all-gather per layer'),
+                          'nnz': int(nnz), 'nnz_max_rank': int(mx[1]), 'key_compile_s': round(t_compile, 3), 'hbm_allocated_gb_max_rank': round(float(mx[2]), 2),
+                          'all_gather_bytes_per_step': int(gather), 'peer_store_fraction': m.peer_store_fraction() if m.fused else None,
+                          'rank0_layer_ms_spmm_barrier': layer_ms, 'l2': 'inputs larger than L2'},
+               'gpu_launches': (len(m.layers) + 2) * K, 'clocks': clocks,
+               'roofline': {'bound': 'hbm', 'kernel': 'whole network (CSR-equivalent algorithmic bytes: 8 B/nnz + activations)', 'achieved': hbm, 'peak': peak * world, 'unit': 'GB/s',
+                            'frac': hbm / (peak * world), 'traffic': None, 'peak_source': peak_src + ' x n_gpus'}}
+        print(json.dumps(out))
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # =================================================================================================
 def main():
     ap = argparse.ArgumentParser()
@@ -248,6 +320,8 @@ def main():
     ap.add_argument('--net', default='acn', choices=['acn', 'lenet', 'vgg16'])
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parallel', default='dp', choices=['dp', 'rows', 'rows-fused'],
+                    help='N > 1: dp = replicas (default); rows = every keyed layer row-sharded + NCCL all-gather; rows-fused = SpMM epilogue stores to NVLink peers')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -265,6 +339,11 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     _native.lib()
+    if args.parallel != 'dp':
+        if world == 1 and not dist.is_initialized():        # single-rank run of the sharded code path (layout / epilogue A-B)
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29533')
+            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', local_rank))
+        return run_row_sharded(args, rank, world, local_rank)
 
     wl = workload(args.net)
     N = args.batch

@@ -54,6 +54,11 @@ int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *total_m
  * to its Y argument: the row-sharded layer writes its slot of every rank's gathered activation buffer from the
  * epilogue, so no separate all-gather runs.  n = 0 restores single-destination stores.  HOST array of device pointers. */
 int kn_output_peers(const uint64_t *peer_y_host, int32_t n);
+/* Same, with a need mask: row_mask[r] (DEVICE memory, one byte per row of the Y argument) has bit i set when peer i
+ * reads output row r in its next layer; only those copies are stored.  A conv layer sharded by pixels then sends its
+ * halo rows to the neighbouring shard and nothing else -- the all-gather of keynet's row-sharded layers (BASELINE
+ * north_star) degenerates to a halo exchange.  row_mask = NULL behaves like kn_output_peers. */
+int kn_output_peers_masked(const uint64_t *peer_y_host, int32_t n, const uint8_t *row_mask);
 
 /* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------
  * Replaces SparseMatrix.torchdot (keynet/sparse.py:488-492 -> scipy csr_matvecs), called from

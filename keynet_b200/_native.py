@@ -13,7 +13,7 @@ KN_SPMM_RELU = 1
 
 # every symbol include/keynet_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    'kn_abi_version', 'kn_last_error', 'kn_device_info', 'kn_output_peers',
+    'kn_abi_version', 'kn_last_error', 'kn_device_info', 'kn_output_peers', 'kn_output_peers_masked',
     'kn_spmm_csr_f32', 'kn_spmm_csr_rows_f32', 'kn_exclusive_scan_i64',
     'kn_csr_row_pattern_hash', 'kn_pg_verify', 'kn_pg_pack', 'kn_spmm_pg_f32',
     'kn_pg_tc_split', 'kn_pg_tc_tensormaps', 'kn_spmm_pg_tc_f32', 'kn_debug_tc_timing',
@@ -54,6 +54,7 @@ def lib():
     L.kn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_int64)]
     sig = {
         'kn_output_peers': [vp, ctypes.c_int32],
+        'kn_output_peers_masked': [vp, ctypes.c_int32, vp],
         'kn_spmm_csr_f32': [vp, vp, vp, i64, i64, vp, i64, vp, i64, i64, u32, vp],
         'kn_spmm_csr_rows_f32': [vp, vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u32, vp],
         'kn_csr_row_pattern_hash': [vp, vp, i64, vp, vp],
@@ -105,9 +106,14 @@ def require_cuda():
         raise NativeError('keynet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
 
 
-def set_output_peers(ptrs):
+def set_output_peers(ptrs, row_mask=None):
     """Fused all-gather: subsequent spmm launches of this thread write every output row to all `ptrs` (device addresses of
-    the same Y slot on every rank); an empty list restores normal stores."""
+    the same Y slot on every rank); an empty list restores normal stores.  row_mask: uint8 CUDA tensor, one byte per
+    output row, bit i = peer i needs the row (None = every row to every peer)."""
     n = len(ptrs)
     arr = (ctypes.c_uint64 * max(n, 1))(*[int(p) for p in ptrs])
-    check(lib().kn_output_peers(arr, n))
+    if row_mask is None:
+        check(lib().kn_output_peers(arr, n))
+    else:
+        assert row_mask.is_cuda and row_mask.dtype.itemsize == 1 and row_mask.is_contiguous()
+        check(lib().kn_output_peers_masked(arr, n, ptr(row_mask)))

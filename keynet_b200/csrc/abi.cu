@@ -39,7 +39,7 @@ KN_API int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *
     return KN_OK;
 }
 
-static thread_local KnPeers g_peers = {0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+static thread_local KnPeers g_peers = {0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr};
 
 KnPeers kn_current_peers() { return g_peers; }
 
@@ -48,5 +48,12 @@ KN_API int kn_output_peers(const uint64_t *peer_y_host, int32_t n) {
     KN_REQUIRE(n == 0 || peer_y_host != nullptr, "output_peers: null pointer list");
     g_peers.n = n;
     for (int i = 0; i < 8; i++) g_peers.y[i] = (i < n) ? reinterpret_cast<float *>(peer_y_host[i]) : nullptr;
+    g_peers.row_mask = nullptr;
     return KN_OK;
+}
+
+KN_API int kn_output_peers_masked(const uint64_t *peer_y_host, int32_t n, const uint8_t *row_mask) {
+    const int rc = kn_output_peers(peer_y_host, n);
+    if (rc == KN_OK && n > 0) g_peers.row_mask = row_mask;
+    return rc;
 }

@@ -34,12 +34,20 @@ static inline int64_t kn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Output replication for the fused SpMM + all-gather (K5): when n > 0 every epilogue stores its rows to all n buffers
 // (its own and the peers' NVLink-mapped ones, same layout everywhere) instead of the single Y it was given.
-struct KnPeers { int n; float *y[8]; };
+// row_mask (optional, device memory, one byte per output row of Y): bit p set = peer p reads this row in the next layer;
+// rows nobody else needs never cross NVLink (the all-gather becomes a halo exchange).  null = every row to every peer.
+struct KnPeers { int n; float *y[8]; const unsigned char *row_mask; };
 // Kernels take it as `const __grid_constant__ KnPeers`, so the pointer list is read straight from the constant bank
 // (a plain by-value struct indexed at run time would be copied to local memory and slow every epilogue).
-#define KN_FOR_EACH_DEST(peers, Y, dst)                                                       \
-    for (int p_ = 0, np_ = ((peers).n > 0 ? (peers).n : 1); p_ < np_; p_++)                   \
-        if (float *dst = ((peers).n > 0 ? (peers).y[p_] : (Y)); true)
+// The mask is loaded by kn_peer_mask() BEFORE the store loop (a load placed between stores is serialised behind them: the
+// compiler must assume the stores alias it, and each row then pays a full L2 round trip).
+__device__ __forceinline__ unsigned kn_peer_mask(const KnPeers &peers, int64_t row) {
+    return (peers.n > 0 && peers.row_mask != nullptr) ? (unsigned)__ldg(peers.row_mask + row) : 0xffu;
+}
+#define KN_FOR_EACH_DEST(peers, Y, mask, dst)                                                 \
+    for (unsigned p_ = 0, np_ = ((peers).n > 0 ? (peers).n : 1); p_ < np_; p_++)              \
+        if (((mask) >> p_) & 1u)                                                              \
+            if (float *dst = ((peers).n > 0 ? (peers).y[p_] : (Y)); true)
 KnPeers kn_current_peers();     // thread-local list set by kn_output_peers() (abi.cu)
 
 // number of SMs of the current device (cached); B200 = 148

@@ -192,7 +192,10 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
                 float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
                 if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                 if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yrow * ldy + n0) = o;
-                else KN_FOR_EACH_DEST(peers, Y, yb) *reinterpret_cast<float4 *>(yb + yrow * ldy + n0) = o;
+                else {
+                    const unsigned pmask = kn_peer_mask(peers, yrow);
+                    KN_FOR_EACH_DEST(peers, Y, pmask, yb) *reinterpret_cast<float4 *>(yb + yrow * ldy + n0) = o;
+                }
             }
         }
     }
@@ -247,14 +250,22 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
             }
         }
         if (ok) {
+            int32_t yrows[GM];
+            unsigned pmask[GM];
+#pragma unroll
+            for (int r = 0; r < GM; r++) yrows[r] = (r < G) ? __ldg(rows + g * G + r) : 0;
+            if (peers.n != 0) {
+#pragma unroll
+                for (int r = 0; r < GM; r++) pmask[r] = kn_peer_mask(peers, yrows[r]);
+            }
 #pragma unroll
             for (int r = 0; r < GM; r++) {
                 if (r < G) {
                     float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                     if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
-                    const int64_t yoff = (int64_t)__ldg(rows + g * G + r) * ldy + n0;
+                    const int64_t yoff = (int64_t)yrows[r] * ldy + n0;
                     if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yoff) = o;
-                    else KN_FOR_EACH_DEST(peers, Y, yb) *reinterpret_cast<float4 *>(yb + yoff) = o;
+                    else KN_FOR_EACH_DEST(peers, Y, pmask[r], yb) *reinterpret_cast<float4 *>(yb + yoff) = o;
                 }
             }
         }

@@ -351,15 +351,37 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ne < n_vecs) {
+                    if constexpr (!PEERS) {
 #pragma unroll
-                    for (int t = 0; t < 16; t++) {
-                        if (c0 + t < g_valid) {
+                        for (int t = 0; t < 16; t++) {
+                            if (c0 + t < g_valid) {
+                                float y = __uint_as_float(r[t]);
+                                if (DUAL) y += __uint_as_float(r2[t]);
+                                if (RELU) y = fmaxf(y, 0.0f);
+                                Y[(int64_t)__ldg(rg + c0 + t) * ldy + ne] = y;
+                            }
+                        }
+                    } else {
+                        // fused all-gather (separate instantiation: this code costs the plain epilogue ~10 %): row ids and
+                        // need masks first, then one pass of NVLink stores per peer
+                        int32_t yrow[16];
+                        unsigned pmask[16];
+#pragma unroll
+                        for (int t = 0; t < 16; t++) yrow[t] = (c0 + t < g_valid) ? __ldg(rg + c0 + t) : -1;
+#pragma unroll
+                        for (int t = 0; t < 16; t++) pmask[t] = (yrow[t] >= 0) ? kn_peer_mask(peers, yrow[t]) : 0u;
+#pragma unroll
+                        for (int t = 0; t < 16; t++) {
                             float y = __uint_as_float(r[t]);
                             if (DUAL) y += __uint_as_float(r2[t]);
                             if (RELU) y = fmaxf(y, 0.0f);
-                            const int64_t yoff = (int64_t)__ldg(rg + c0 + t) * ldy + ne;
-                            if constexpr (!PEERS) Y[yoff] = y;                                  // (separate instantiation: the peer loop
-                            else KN_FOR_EACH_DEST(peers, Y, yb) yb[yoff] = y;                   //  costs the plain epilogue ~10 %) NVLink peer stores
+                            r[t] = __float_as_uint(y);
+                        }
+                        for (int p = 0; p < peers.n; p++) {
+                            float *__restrict__ yb = peers.y[p];
+#pragma unroll
+                            for (int t = 0; t < 16; t++)
+                                if ((pmask[t] >> p) & 1u) yb[(int64_t)yrow[t] * ldy + ne] = __uint_as_float(r[t]);
                         }
                     }
                 }

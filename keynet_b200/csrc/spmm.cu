@@ -101,8 +101,9 @@ spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
 #pragma unroll
             for (int i = 0; i < V; i++) acc[i] = fmaxf(acc[i], 0.0f);
         }
-        const int64_t yoff = (out_rows ? (int64_t)out_rows[row] : row) * ldy + n0;
-        KN_FOR_EACH_DEST(peers, Y, yb) {                         // fused all-gather: the row goes to every peer's buffer
+        const int64_t yrow = out_rows ? (int64_t)out_rows[row] : row;
+        const int64_t yoff = yrow * ldy + n0;
+        KN_FOR_EACH_DEST(peers, Y, kn_peer_mask(peers, yrow), yb) {                         // fused all-gather: the row goes to every peer's buffer
             float *yp = yb + yoff;
             if constexpr (V == 4) *reinterpret_cast<float4 *>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             else if constexpr (V == 2) *reinterpret_cast<float2 *>(yp) = make_float2(acc[0], acc[1]);
@@ -123,6 +124,7 @@ spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restr
     if (row >= n_rows) return;
     const int64_t beg = indptr[row], end = indptr[row + 1];
     const int64_t yrow = out_rows ? (int64_t)out_rows[row] : row;
+    const unsigned pmask = kn_peer_mask(peers, yrow);
     float acc[NB];
 #pragma unroll
     for (int n = 0; n < NB; n++) acc[n] = 0.0f;
@@ -143,7 +145,7 @@ spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restr
     for (int n = 0; n < NB; n++)
         if (lane == n && n < n_vecs) {
             const float o = RELU ? fmaxf(acc[n], 0.0f) : acc[n];
-            KN_FOR_EACH_DEST(peers, Y, yb) yb[yrow * ldy + n] = o;
+            KN_FOR_EACH_DEST(peers, Y, pmask, yb) yb[yrow * ldy + n] = o;
         }
 }
 

@@ -19,29 +19,49 @@ import torch
 from torch import nn
 
 
-def plan_rows(module, outshape, world):
-    """Shard-major order of the canonical output rows of one layer (homogeneous row excluded).
+def plan_rows(module, outshape, world, A=None):
+    """Shard-major order of the output rows of one keyed layer W_hat = A.W.Ainv (homogeneous row excluded).
 
-    Returns (order, chunk): `order` = canonical row indices, pixel-major for convolutions so that chunk boundaries
-    fall between pattern groups; rank r owns order[r*chunk:(r+1)*chunk] (the last ranks may own fewer / no rows)."""
+    Returns (order, chunk): `order` = row indices of W_hat; rank r owns order[r*chunk:(r+1)*chunk] (the last ranks may
+    own fewer / no rows).  Spatial layers are cut by the PIXEL of the underlying Toeplitz row (row r of W_hat is row
+    A.perm[r] of W), raster order, all channels of a pixel together: chunk boundaries fall between pattern groups, and
+    a shard reads only its own pixels plus a halo of the previous layer whatever permutation the keys apply -- which is
+    what lets the fused path (peer row masks) replace the all-gather by a halo exchange."""
     (C, H, W) = [int(s) for s in outshape]
     R = C * H * W
-    if isinstance(module, nn.Conv2d) and H * W > 1:
-        order = np.arange(R, dtype=np.int64).reshape(C, H * W).T.reshape(-1)      # (pixel, channel) <- (channel, pixel)
+    src = np.arange(R, dtype=np.int64) if A is None else np.asarray(A.perm[:R], dtype=np.int64)   # Toeplitz row of every W_hat row
+    assert A is None or (len(A.perm) == R + 1 and src.max() < R), 'output key must be homogeneous'
+    if isinstance(module, (nn.Conv2d, nn.AvgPool2d)) and H * W > 1:
+        (channel, pixel) = (src // (H * W), src % (H * W))
+        order = np.argsort(pixel * C + channel, kind='stable').astype(np.int64)       # (pixel, channel) <- (channel, pixel)
         px_chunk = -(-(H * W) // world)
         chunk = px_chunk * C
     else:
-        order = np.arange(R, dtype=np.int64)
+        order = np.argsort(src, kind='stable').astype(np.int64)
         chunk = -(-R // world)
     return (order, int(chunk))
+
+
+def peer_row_masks(need, rank, chunk, n_mine):
+    """need: bool [world, n_phys] -- need[q, p] = rank q reads gathered position p in its next layer.  Returns the
+    uint8 mask of this rank's n_mine output rows: bit q set = store the row into rank q's buffer (own bit always set)."""
+    need = np.asarray(need, dtype=bool)
+    world = need.shape[0]
+    assert world <= 8
+    mine = need[:, rank * chunk:rank * chunk + n_mine]
+    mask = np.zeros(n_mine, dtype=np.uint8)
+    for q in range(world):
+        mask |= (mine[q].astype(np.uint8) << q).astype(np.uint8)
+    mask |= np.uint8(1 << rank)
+    return mask
 
 
 class LayerShard(object):
     """Bookkeeping of one row-sharded layer: which canonical rows this rank computes and where every canonical row
     lives in the gathered buffer [world*chunk + 1] (last position = homogeneous coordinate)."""
 
-    def __init__(self, module, outshape, rank, world):
-        (order, chunk) = plan_rows(module, outshape, world)
+    def __init__(self, module, outshape, rank, world, A=None):
+        (order, chunk) = plan_rows(module, outshape, world, A)
         R = len(order)
         self.chunk = chunk
         self.n_phys = world * chunk + 1
@@ -57,17 +77,18 @@ class ShardedLayerGen(object):
     """f_module_to_keyedmodule callback for system.KeyedModel: compiles, for every keyed layer, only this rank's rows
     with the previous layer's gathered layout folded into the column map."""
 
-    def __init__(self, rank, world, inshape):
+    def __init__(self, rank, world, inshape, keep_csr=True):
         (self.rank, self.world) = (int(rank), int(world))
+        self.keep_csr = keep_csr
         self.prev_position = None            # first layer reads the sensor output in canonical order
         self.prev_n_phys = int(np.prod(inshape)) + 1
         self.layers = []
 
     def __call__(self, module, inshape, outshape, A, Ainv):
         from . import layer as _layer
-        shard = LayerShard(module, outshape, self.rank, self.world)
+        shard = LayerShard(module, outshape, self.rank, self.world, A)
         L = _layer.KeyedLayer(module, inshape, outshape, A, Ainv, rows=shard.my_rows,
-                              col_remap=self.prev_position, n_cols_phys=self.prev_n_phys)
+                              col_remap=self.prev_position, n_cols_phys=self.prev_n_phys, keep_csr=self.keep_csr)
         L._shard = shard
         (self.prev_position, self.prev_n_phys) = (shard.position, shard.n_phys)
         self.layers.append(L)
@@ -77,20 +98,57 @@ class ShardedLayerGen(object):
 class ShardedKeyedModel(object):
     """Row-sharded keyed network: same constructor contract as system.Keynet(...)[1] plus (rank, world, group)."""
 
-    def __init__(self, inshape, net, rank, world, group=None, fused=False, **keynet_kwargs):
+    def __init__(self, inshape, net, rank, world, group=None, fused=False, selective=True, keep_csr=True, **keynet_kwargs):
         """fused=True: no NCCL on the data path -- every SpMM epilogue stores its rows straight into all ranks' gathered
         activation buffers (torch symmetric memory = NVLink peer mappings, kn_output_peers), one device-side barrier per
-        layer.  fused=False: local SpMM + torch.distributed all_gather_into_tensor (NCCL)."""
+        layer; with selective=True (default) a row is stored only into the buffers of the ranks whose next layer reads it
+        (kn_output_peers_masked).  fused=False: local SpMM + torch.distributed all_gather_into_tensor (NCCL)."""
         from . import system
         self.rank, self.world, self.group = int(rank), int(world), group
-        self.fused = bool(fused) and self.world > 1
+        self.fused = bool(fused)
+        self.selective = bool(selective)       # fused only: store a row only to the peers whose next layer reads it
         self._symm = {}
         f_keypair = system.keypair_policy(**keynet_kwargs)
         self.sensor = system.KeyedSensor(inshape, f_keypair('input', inshape))
-        self._gen = ShardedLayerGen(rank, world, inshape)
+        self._gen = ShardedLayerGen(rank, world, inshape, keep_csr=keep_csr)
         self._model = system.KeyedModel(net, inshape, self.sensor.key(), f_keypair, self._gen)
         self._outshape = self._model._outshape
         self.layers = self._gen.layers
+        self._masks = None
+        self.time_layers = False      # record CUDA events around every layer (SpMM + barrier / all-gather)
+        self._events = []
+
+    def _peer_masks(self, dev):
+        """Per layer: which peers read each of this rank's output rows (one all-gather of need bitmaps at set-up)."""
+        if self._masks is None:
+            import torch.distributed as dist
+            group = self.group if self.group is not None else dist.group.WORLD
+            masks = []
+            for (k, L) in enumerate(self.layers):
+                sh = L._shard
+                n_mine = len(sh.my_rows)
+                if k + 1 < len(self.layers):
+                    need = self.layers[k + 1].W.used_columns().to(torch.uint8)
+                    assert need.numel() == sh.n_phys
+                    allneed = torch.empty((self.world, sh.n_phys), dtype=torch.uint8, device=dev)
+                    dist.all_gather_into_tensor(allneed, need.reshape(1, -1).contiguous(), group=group)
+                    m = peer_row_masks(allneed.cpu().numpy() != 0, self.rank, sh.chunk, n_mine)
+                else:
+                    m = np.full(n_mine, (1 << self.world) - 1, dtype=np.uint8)      # the logits go to everyone
+                masks.append(torch.from_numpy(m).to(dev))
+            self._masks = masks
+        return self._masks
+
+    def peer_store_fraction(self):
+        """Rows x destinations actually stored / (rows x world): 1.0 = full all-gather."""
+        if self._masks is None:
+            return None
+        (sent, full) = (0, 0)
+        for (L, m) in zip(self.layers, self._masks):
+            bits = m.cpu().numpy()
+            sent += int(np.unpackbits(bits.reshape(-1, 1), axis=1).sum())
+            full += len(bits) * self.world
+        return sent / max(full, 1)
 
     def num_parameters_local(self):
         return sum(L.nnz() for L in self.layers)
@@ -114,23 +172,44 @@ class ShardedKeyedModel(object):
         from . import _native
         from .sparse import spmm
         bufs = self._symm_buffers(N, dev)
+        masks = self._peer_masks(dev) if self.selective else [None] * len(self.layers)
         for (k, L) in enumerate(self.layers):
             sh = L._shard
             relu = L._fused_relu or ('ReLU' in L._layertype)
+            self._stamp()
             (t, h) = bufs[k % 2]
             Yfull = t[:sh.n_phys * N].view(sh.n_phys, N)
             n_mine = len(sh.my_rows)
             slot = self.rank * sh.chunk * N * 4                         # byte offset of this rank's slot in every buffer
             if n_mine > 0:
-                _native.set_output_peers([int(p) + slot for p in h.buffer_ptrs])
+                _native.set_output_peers([int(p) + slot for p in h.buffer_ptrs], masks[k])
                 try:
                     spmm(L.W, X, relu=relu, out=Yfull[self.rank * sh.chunk:self.rank * sh.chunk + n_mine])
                 finally:
                     _native.set_output_peers([])
             Yfull[-1].fill_(1.0)                                        # homogeneous coordinate: local
+            self._stamp()
             h.barrier()                                                 # every rank's stores have landed everywhere
             X = Yfull
+        self._stamp()
         return X
+
+    def _stamp(self):
+        if self.time_layers:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._events.append(e)
+
+    def layer_times_ms(self):
+        """time_layers=True: [(layer, spmm_ms, barrier / all-gather ms)] of the LAST forward."""
+        torch.cuda.synchronize()
+        n = len(self.layers)
+        ev = self._events[-(2 * n + 1):]
+        out = []
+        for k in range(n):
+            out.append((k, ev[2 * k].elapsed_time(ev[2 * k + 1]), ev[2 * k + 1].elapsed_time(ev[2 * k + 2])))
+        self._events = []
+        return out
 
     def forward_linear(self, x_cipher):
         """x_cipher: N x (D+1) encrypted batch, identical on every rank.  Returns N x (K+1) on every rank."""
@@ -146,6 +225,7 @@ class ShardedKeyedModel(object):
         for L in self.layers:
             sh = L._shard
             relu = L._fused_relu or ('ReLU' in L._layertype)
+            self._stamp()
             Yfull = torch.empty((sh.n_phys, N), dtype=torch.float32, device=dev)
             Yloc = Yfull[self.rank * sh.chunk:(self.rank + 1) * sh.chunk]       # this rank's slot of the gathered buffer
             n_mine = len(sh.my_rows)
@@ -153,10 +233,12 @@ class ShardedKeyedModel(object):
                 Yloc[n_mine:].zero_()
             if n_mine > 0:
                 spmm(L.W, X, relu=relu, out=Yloc[:n_mine])
+            self._stamp()
             if self.world > 1:
                 dist.all_gather_into_tensor(Yfull[:self.world * sh.chunk], Yloc, group=self.group)
             Yfull[-1].fill_(1.0)                                      # homogeneous coordinate: local, never communicated
             X = Yfull
+        self._stamp()
         # last layer: undo the shard-major order (a gather of K+1 rows)
         pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
         return X[pos].t().contiguous()

@@ -439,6 +439,17 @@ class SparseMatrix(object):
         D[np.repeat(np.arange(self.shape[0]), np.diff(ip)), ix] = dt
         return D
 
+    def used_columns(self):
+        """bool CUDA tensor [n_cols]: columns some stored entry (or padded slot of the grouped format) reads."""
+        if self._pg is not None:
+            lists = [c['cols'] for c in self._pg.classes] + ([self._pg.rest['indices']] if self._pg.rest is not None else [])
+        else:
+            lists = [self._indices[int(self._indptr[0]):int(self._indptr[-1])]]
+        used = torch.zeros(self.shape[1], dtype=torch.bool, device=lists[0].device)
+        for ix in lists:
+            used[ix.to(torch.int64)] = True
+        return used
+
     def optimize(self, min_group=4, min_nnz=4096):
         """Build the pattern-grouped execution format (csrc/pgroup.cu) next to the canonical CSR.  The CSR stays
         the source of truth (parity, export, small batches); batches of >= 32 images run on the groups."""

@@ -14,6 +14,7 @@ from torch import nn
 
 from keynet_b200 import dist as kdist
 from keynet_b200 import system, nets
+from keynet_b200.sparse import MonomialKey
 from oracle import keynet_oracle as ko
 
 
@@ -54,7 +55,7 @@ def _oracle_net(seed=0):
         class Rec(nn.Module):
             def fuse_relu(self, flag=True):
                 self.relu = bool(flag); return self
-        r = Rec(); r.W = What; r.relu = False; r.module = module; r.outshape = oshape
+        r = Rec(); r.W = What; r.relu = False; r.module = module; r.outshape = oshape; r.A = A
         layers.append(r)
         return r
     np.random.seed(seed)
@@ -89,11 +90,17 @@ def _worker(rank, world, port, q):
         Xr = X
         for L in layers:
             Xr = ko.spmm(L.W, Xr, relu=L.relu)
-        # sharded
+        # sharded: compile every layer's shard first (rows cut by the pixel of the underlying Toeplitz row, the previous
+        # layer's gathered layout folded into the columns), then derive who needs which gathered row
         (pos_prev, n_prev) = (None, X.shape[0])
+        (shards, Wls) = ([], [])
         for L in layers:
-            sh = kdist.LayerShard(L.module, L.outshape, rank, world)
-            Wl = _shard_csr(L.W, sh.my_rows, pos_prev, n_prev)
+            sh = kdist.LayerShard(L.module, L.outshape, rank, world, L.A)
+            Wls.append(_shard_csr(L.W, sh.my_rows, pos_prev, n_prev))
+            shards.append(sh)
+            (pos_prev, n_prev) = (sh.position, sh.n_phys)
+        sent = full = 0
+        for (k, (L, sh, Wl)) in enumerate(zip(layers, shards, Wls)):
             Yloc = np.zeros((sh.chunk, X.shape[1]), dtype=np.float32)
             if len(sh.my_rows):
                 Yloc[:len(sh.my_rows)] = ko.spmm(Wl, X, relu=L.relu)
@@ -101,7 +108,21 @@ def _worker(rank, world, port, q):
             dist.all_gather_into_tensor(Yfull[:world * sh.chunk], torch.from_numpy(Yloc))
             Yfull[-1] = 1.0
             X = Yfull.numpy()
-            (pos_prev, n_prev) = (sh.position, sh.n_phys)
+            if k + 1 < len(layers):
+                # selective peer stores (kn_output_peers_masked): a rank only ever receives the rows its next layer reads.
+                # Emulated by poisoning everything else after the gather -- the result must not change.
+                need = np.zeros(sh.n_phys, dtype=bool)
+                need[Wls[k + 1].indices] = True
+                allneed = [None] * world
+                dist.all_gather_object(allneed, need)
+                allneed = np.stack(allneed)
+                mask = kdist.peer_row_masks(allneed, rank, sh.chunk, len(sh.my_rows))
+                for peer in range(world):
+                    want = allneed[peer, rank * sh.chunk:rank * sh.chunk + len(sh.my_rows)] | (peer == rank)
+                    assert np.array_equal((mask >> peer) & 1, want.astype(np.uint8))
+                sent += int(np.unpackbits(mask.reshape(-1, 1), axis=1).sum()); full += len(mask) * world
+                own = np.zeros(sh.n_phys, dtype=bool); own[rank * sh.chunk:(rank + 1) * sh.chunk] = True; own[-1] = True
+                X[~(need | own)] = np.nan
         Y = X[pos_prev]
         # the gathered layout re-orders the columns inside a row, i.e. the fp32 summation order: equal to rounding
         q.put((rank, bool(np.allclose(Y, Xr, rtol=1e-5, atol=1e-6)), float(np.abs(Y - Xr).max())))
@@ -128,18 +149,24 @@ def test_row_sharded_forward_equals_unsharded_world2():
 def test_shard_plan_properties():
     for (module, outshape) in [(nn.Conv2d(3, 8, 3, padding=1), (8, 5, 7)), (nn.AvgPool2d(3, 2, 1), (4, 6, 6)), (nn.Linear(10, 13), (13, 1, 1)),
                                (nn.Conv2d(3, 8, 3, padding=1), (8, 1, 1))]:
-        for world in (1, 2, 3, 8):
-            shards = [kdist.LayerShard(module, outshape, r, world) for r in range(world)]
+        for (world, keyed) in [(1, False), (2, False), (2, True), (3, True), (8, False), (8, True)]:
             R = int(np.prod(outshape))
+            A = MonomialKey(np.concatenate([np.random.RandomState(world).permutation(R), [R]])) if keyed else None
+            shards = [kdist.LayerShard(module, outshape, r, world, A) for r in range(world)]
             got = np.concatenate([s.my_rows for s in shards])
             assert np.array_equal(np.sort(got), np.arange(R))                 # every canonical row owned exactly once
             for (r, s) in enumerate(shards):
                 assert len(s.my_rows) <= s.chunk and s.n_phys == world * s.chunk + 1
                 assert np.array_equal(s.position[s.my_rows], r * s.chunk + np.arange(len(s.my_rows)))
                 assert s.position[R] == world * s.chunk
-            if isinstance(module, nn.Conv2d) and outshape[1] * outshape[2] > 1:
-                # conv shards hold whole pattern groups: all output channels of each owned pixel
+            if isinstance(module, (nn.Conv2d, nn.AvgPool2d)) and outshape[1] * outshape[2] > 1:
+                # spatial shards hold whole pattern groups: all output channels of each owned pixel of the underlying
+                # Toeplitz matrix, and the pixels of rank r precede those of rank r+1 in raster order
+                last = -1
                 for s in shards:
-                    px = s.my_rows % (outshape[1] * outshape[2])
+                    px = (s.my_rows if A is None else A.perm[s.my_rows]) % (outshape[1] * outshape[2])
+                    if len(px):
+                        assert px.min() > last
+                        last = px.max()
                     assert len(s.my_rows) % outshape[0] == 0
                     assert all(np.sum(px == p) == outshape[0] for p in np.unique(px))

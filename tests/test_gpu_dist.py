@@ -35,7 +35,7 @@ def test_sharded_model_world1_matches_unsharded():
     assert np.allclose(y, _net()(x).detach().numpy(), atol=1e-4)
 
 
-def _worker(rank, world, port, q, fused=False):
+def _worker(rank, world, port, q, fused=False, selective=True):
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -45,29 +45,36 @@ def _worker(rank, world, port, q, fused=False):
         x = torch.randn(64, 1, 28, 28, generator=torch.Generator().manual_seed(1))
         (xc, y_ref) = _reference(x)
         np.random.seed(0)
-        m = kdist.ShardedKeyedModel((1, 28, 28), _net(), rank=rank, world=world, fused=fused, global_geometric='permutation', global_photometric='uniform_random_gain', beta=1.0)
+        m = kdist.ShardedKeyedModel((1, 28, 28), _net(), rank=rank, world=world, fused=fused, selective=selective, global_geometric='permutation', global_photometric='uniform_random_gain', beta=1.0)
+        if fused and selective:                                # rows no peer asked for must never be read: poison the buffers
+            for (t, h) in m._symm_buffers(64, torch.device('cuda', rank)):
+                t.fill_(float('nan'))
+            dist.barrier()
         y = m.forward(xc).reshape(64, -1).cpu().numpy()
         y = m.forward(xc).reshape(64, -1).cpu().numpy()       # twice: ping-pong buffers are reused
-        q.put((rank, bool(np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)), float(np.abs(y - y_ref).max()), m.num_parameters_local()))
+        q.put((rank, bool(np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)), float(np.abs(y - y_ref).max()), m.num_parameters_local(), m.peer_store_fraction()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('fused', [False, True])
-def test_sharded_model_world2(fused):
-    """fused=False: NCCL all-gather per layer; fused=True: epilogue stores to peer memory (K5), no NCCL on the data path."""
+@pytest.mark.parametrize('fused,selective', [(False, False), (True, False), (True, True)])
+def test_sharded_model_world2(fused, selective):
+    """fused=False: NCCL all-gather per layer; fused=True: epilogue stores to peer memory (K5), no NCCL on the data path;
+    selective: only the rows a peer's next layer reads are stored to it (halo exchange instead of all-gather)."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, fused)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, fused, selective)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for (rank, ok, err, nnz) in res:
+    for (rank, ok, err, nnz, frac) in res:
         assert ok, (rank, err)
+        if fused and selective:
+            assert frac is not None and frac < 0.95, frac          # fewer stores than a full all-gather
     assert abs(res[0][3] - res[1][3]) < 0.2 * max(res[0][3], res[1][3])      # shards are balanced
