@@ -95,6 +95,21 @@ int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data,
 int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
+/* Clustered variant for small groups (G <= 16; csrc/pgcluster.cu): the groups of a tile of neighbouring output pixels
+ * form a cluster with ONE union column list that is staged in shared memory once per (cluster, 128 batch columns), so a
+ * 3x3 convolution reads every X row from L2 about once instead of 9 times.
+ *   cl_gptr[n_clusters+1]   group range of every cluster (groups are stored cluster by cluster)
+ *   cl_uptr[n_clusters+1]   range of every cluster in ucols; at most KN_CG_MAX_UNION columns per cluster
+ *   ucols                   union column lists
+ *   lidx[n_groups][K_pad]   BYTE offset (local column index x 512) of every column of the group in the staged tile
+ *   valsT[n_blocks][K_pad][GM]  value blocks k-major, GM = G rounded up to even (zero padded)
+ * rows / group_k / block_of as in kn_spmm_pg_f32.  u_max / g_max = largest union / group count of a cluster: the CTA stages
+ * u_max x 512 B of X plus g_max x K_pad x 4 B of lidx, together at most KN_CG_MAX_UNION x 512 B. */
+#define KN_CG_MAX_UNION 224
+int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t *ucols, const int32_t *rows, const int32_t *lidx, const float *valsT,
+                   const int32_t *group_k, const int32_t *block_of, int64_t n_clusters, int32_t G, int32_t K_pad, int32_t u_max, int32_t g_max,
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+
 /* Tensor-core variant (csrc/pgroup_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo),
  * fp32 accumulators in TMEM, weight blocks by TMA, gathered activations written into the UMMA layout by producer
  * warps.  kn_pg_tc_split: vals -> (hi = v & 0xffffe000, lo = v - hi); kn_pg_tc_tensormaps: writes four CUtensorMap

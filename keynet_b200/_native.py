@@ -15,7 +15,7 @@ KN_SPMM_RELU = 1
 SYMBOLS = [
     'kn_abi_version', 'kn_last_error', 'kn_device_info', 'kn_output_peers', 'kn_output_peers_masked',
     'kn_spmm_csr_f32', 'kn_spmm_csr_rows_f32', 'kn_exclusive_scan_i64',
-    'kn_csr_row_pattern_hash', 'kn_pg_verify', 'kn_pg_pack', 'kn_spmm_pg_f32',
+    'kn_csr_row_pattern_hash', 'kn_pg_verify', 'kn_pg_pack', 'kn_spmm_pg_f32', 'kn_spmm_cg_f32',
     'kn_pg_tc_split', 'kn_pg_tc_tensormaps', 'kn_spmm_pg_tc_f32', 'kn_debug_tc_timing',
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
@@ -61,6 +61,7 @@ def lib():
         'kn_pg_verify': [vp, vp, vp, vp, i64, vp, vp],
         'kn_pg_pack': [vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp],
         'kn_spmm_pg_f32': [vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
+        'kn_spmm_cg_f32': [vp, vp, vp, vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_debug_tc_timing': [ctypes.c_int32, vp],
         'kn_pg_tc_split': [vp, i64, vp, vp, vp],
         'kn_pg_tc_tensormaps': [vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp],

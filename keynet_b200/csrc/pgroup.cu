@@ -206,7 +206,7 @@ pg_simt_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ col
 // walks the 128-column batch tiles of its super-tile: per k one coalesced LDG.128 of the gathered X row segment
 // feeds 4*G FFMA (values come as warp-broadcast LDS.128), exact K (no padding), G rows x 512 B written per tile.
 template <int GM, bool RELU>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ cols, const float *__restrict__ vals,
                 const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_groups, int G, int K_pad, int64_t n_supers, int tiles_per_super,
                 const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
@@ -222,10 +222,13 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
     const int K = group_k ? __ldg(group_k + g) : K_pad;
     const int64_t blk = block_of ? (int64_t)__ldg(block_of + g) : g;
 
-    for (int i = lane; i < K; i += 32) s_col[i] = __ldg(cols + g * (int64_t)K_pad + i);
-    for (int i = lane; i < K * GM; i += 32) {
+    // K rounded up to the prefetch block with zero values / a valid column: the k loop carries no predicates
+    constexpr int PD = (GM <= 8) ? 8 : 4;                                    // gathered X rows in flight per lane: 2 x PD LDG.128
+    const int Kr = (K + 2 * PD - 1) / (2 * PD) * (2 * PD);                   // <= K_pad (a multiple of 32)
+    for (int i = lane; i < Kr; i += 32) s_col[i] = __ldg(cols + g * (int64_t)K_pad + (i < K ? i : 0));
+    for (int i = lane; i < Kr * GM; i += 32) {
         const int k = i / GM, r = i - k * GM;
-        s_val[i] = (r < G) ? __ldg(vals + (blk * G + r) * (int64_t)K_pad + k) : 0.0f;
+        s_val[i] = (r < G && k < K) ? __ldg(vals + (blk * G + r) * (int64_t)K_pad + k) : 0.0f;
     }
     __syncwarp();
 
@@ -237,9 +240,10 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
         float acc[GM][4];
 #pragma unroll
         for (int r = 0; r < GM; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f; }
-#pragma unroll 2
-        for (int k = 0; k < K; k++) {
-            const float4 x = ok ? __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)s_col[k] * ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // one coalesced LDG.128 per k feeds 4*GM FFMA; with a single load in flight the loop is bound by L2 latency, so
+        // the gathers run a double-buffered register ring 2 x PD rows ahead of the FMAs
+        auto gather = [&](int k) { return __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)s_col[k] * ldx)); };
+        auto fma_row = [&](const float4 x, int k) {
 #pragma unroll
             for (int r4 = 0; r4 < GM; r4 += 4) {
                 const float4 a = *reinterpret_cast<const float4 *>(&s_val[k * GM + r4]);
@@ -248,24 +252,43 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
                 acc[r4 + 2][0] = fmaf(a.z, x.x, acc[r4 + 2][0]); acc[r4 + 2][1] = fmaf(a.z, x.y, acc[r4 + 2][1]); acc[r4 + 2][2] = fmaf(a.z, x.z, acc[r4 + 2][2]); acc[r4 + 2][3] = fmaf(a.z, x.w, acc[r4 + 2][3]);
                 acc[r4 + 3][0] = fmaf(a.w, x.x, acc[r4 + 3][0]); acc[r4 + 3][1] = fmaf(a.w, x.y, acc[r4 + 3][1]); acc[r4 + 3][2] = fmaf(a.w, x.z, acc[r4 + 3][2]); acc[r4 + 3][3] = fmaf(a.w, x.w, acc[r4 + 3][3]);
             }
-        }
-        if (ok) {
-            int32_t yrows[GM];
-            unsigned pmask[GM];
+        };
+        float4 xa[PD], xc[PD];
 #pragma unroll
-            for (int r = 0; r < GM; r++) yrows[r] = (r < G) ? __ldg(rows + g * G + r) : 0;
-            if (peers.n != 0) {
+        for (int i = 0; i < PD; i++) xa[i] = gather(i);
+        for (int k0 = 0; k0 < Kr; k0 += 2 * PD) {
 #pragma unroll
-                for (int r = 0; r < GM; r++) pmask[r] = kn_peer_mask(peers, yrows[r]);
+            for (int i = 0; i < PD; i++) xc[i] = gather(k0 + PD + i);
+#pragma unroll
+            for (int i = 0; i < PD; i++) fma_row(xa[i], k0 + i);
+            if (k0 + 2 * PD < Kr) {
+#pragma unroll
+                for (int i = 0; i < PD; i++) xa[i] = gather(k0 + 2 * PD + i);
             }
 #pragma unroll
-            for (int r = 0; r < GM; r++) {
-                if (r < G) {
-                    float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                    if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
-                    const int64_t yoff = (int64_t)yrows[r] * ldy + n0;
-                    if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yoff) = o;
-                    else KN_FOR_EACH_DEST(peers, Y, pmask[r], yb) *reinterpret_cast<float4 *>(yb + yoff) = o;
+            for (int i = 0; i < PD; i++) fma_row(xc[i], k0 + PD + i);
+        }
+        if (ok) {
+#pragma unroll
+            for (int r4 = 0; r4 < GM; r4 += 4) {                              // row ids / need masks of 4 rows, then their stores
+                int32_t yrows[4];
+                unsigned pmask[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) yrows[i] = (r4 + i < G) ? __ldg(rows + g * G + r4 + i) : 0;
+                if (peers.n != 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) pmask[i] = kn_peer_mask(peers, yrows[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r = r4 + i;
+                    if (r < G) {
+                        float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                        if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        const int64_t yoff = (int64_t)yrows[i] * ldy + n0;
+                        if (peers.n == 0) *reinterpret_cast<float4 *>(Y + yoff) = o;
+                        else KN_FOR_EACH_DEST(peers, Y, pmask[i], yb) *reinterpret_cast<float4 *>(yb + yoff) = o;
+                    }
                 }
             }
         }
@@ -276,8 +299,12 @@ template <int GM>
 int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
                  const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
-    const int tiles_per_super = 16;                                          // 2048 batch columns per warp work item
-    const int64_t n_tiles = kn_cdiv(n_vecs, TN), n_supers = kn_cdiv(n_tiles, tiles_per_super);
+    // up to 2048 batch columns per warp work item (the group's values are staged once per item), fewer when that would
+    // leave the grid with only a few waves of CTAs (tail effect: LeNet conv2 has 196 groups)
+    int tiles_per_super = 16;
+    const int64_t n_tiles = kn_cdiv(n_vecs, TN);
+    while (tiles_per_super > 2 && n_groups * kn_cdiv(n_tiles, tiles_per_super) < (int64_t)kn_sm_count() * 2 * 8 * (kThreads / 32)) tiles_per_super /= 2;
+    const int64_t n_supers = kn_cdiv(n_tiles, tiles_per_super);
     const int64_t n_items = n_groups * n_supers, gx = kn_cdiv(n_items, kThreads / 32);
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm_pg(small): grid too large");
     const size_t smem = (size_t)(kThreads / 32) * K_pad * (GM + 1) * sizeof(float);

@@ -16,6 +16,7 @@
 //   * lanes_nnz<NB> (N <= 8): one warp per row, lanes stride over the row's entries (coalesced
 //     index/value reads), NB accumulators per lane, warp-shuffle tree reduction at the end.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -112,6 +113,80 @@ spmm_rowwarp_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
     }
 }
 
+// Wide variant for large batches: the warp covers WS consecutive 128-column segments (WS x 512 B contiguous per gathered
+// X row).  A 512-byte piece per row keeps too few bytes in flight per warp for short rows (a permutation key has ONE entry
+// per row: three dependent loads to move 512 B) and opens a new DRAM page per piece; 2 KB per row quadruples the bytes in
+// flight and reads whole pages.
+template <int WS, bool RELU>
+__global__ void __launch_bounds__(kWarps * 32, (WS <= 2) ? 6 : 4)
+spmm_rowwarp_wide_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                         const float *__restrict__ data, int64_t n_rows,
+                         const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs,
+                         const int32_t *__restrict__ out_rows, const __grid_constant__ KnPeers peers)
+{
+    __shared__ int2 s_ent[kWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
+    if (row >= n_rows) return;                                   // warp-uniform
+    const int64_t n0 = (int64_t)blockIdx.y * (WS * 128) + lane * 4;
+    const int64_t beg = indptr[row], end = indptr[row + 1];
+    bool act[WS];
+#pragma unroll
+    for (int s = 0; s < WS; s++) act[s] = n0 + s * 128 < n_vecs;
+    float acc[WS][4];
+#pragma unroll
+    for (int s = 0; s < WS; s++) { acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.0f; }
+
+    for (int64_t base = beg; base < end; base += 32) {
+        const int64_t e = base + lane;
+        int c = 0; float w = 0.0f;
+        if (e < end) { c = kn_ldg_stream_i32(indices + e); w = kn_ldg_stream_f32(data + e); }
+        s_ent[warp][lane] = make_int2(c, __float_as_int(w));
+        __syncwarp();
+        const int cnt = (int)((end - base) < 32 ? (end - base) : 32);
+        int t = 0;
+        for (; t + 2 <= cnt; t += 2) {                                         // 2 x WS gathers in flight per lane
+            const int2 p0 = s_ent[warp][t], p1 = s_ent[warp][t + 1];
+            const float *__restrict__ x0p = X + (int64_t)p0.x * ldx + n0, *__restrict__ x1p = X + (int64_t)p1.x * ldx + n0;
+            float4 x0[WS], x1[WS];
+#pragma unroll
+            for (int s = 0; s < WS; s++) x0[s] = act[s] ? __ldg(reinterpret_cast<const float4 *>(x0p + s * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int s = 0; s < WS; s++) x1[s] = act[s] ? __ldg(reinterpret_cast<const float4 *>(x1p + s * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float w0 = __int_as_float(p0.y), w1 = __int_as_float(p1.y);
+#pragma unroll
+            for (int s = 0; s < WS; s++) {
+                acc[s][0] = fmaf(w0, x0[s].x, acc[s][0]); acc[s][1] = fmaf(w0, x0[s].y, acc[s][1]); acc[s][2] = fmaf(w0, x0[s].z, acc[s][2]); acc[s][3] = fmaf(w0, x0[s].w, acc[s][3]);
+            }
+#pragma unroll
+            for (int s = 0; s < WS; s++) {
+                acc[s][0] = fmaf(w1, x1[s].x, acc[s][0]); acc[s][1] = fmaf(w1, x1[s].y, acc[s][1]); acc[s][2] = fmaf(w1, x1[s].z, acc[s][2]); acc[s][3] = fmaf(w1, x1[s].w, acc[s][3]);
+            }
+        }
+        if (t < cnt) {
+            const int2 p0 = s_ent[warp][t];
+            const float *__restrict__ x0p = X + (int64_t)p0.x * ldx + n0;
+            const float w0 = __int_as_float(p0.y);
+#pragma unroll
+            for (int s = 0; s < WS; s++) {
+                const float4 x = act[s] ? __ldg(reinterpret_cast<const float4 *>(x0p + s * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[s][0] = fmaf(w0, x.x, acc[s][0]); acc[s][1] = fmaf(w0, x.y, acc[s][1]); acc[s][2] = fmaf(w0, x.z, acc[s][2]); acc[s][3] = fmaf(w0, x.w, acc[s][3]);
+            }
+        }
+        __syncwarp();
+    }
+    const int64_t yrow = out_rows ? (int64_t)out_rows[row] : row;
+    const unsigned pmask = kn_peer_mask(peers, yrow);
+#pragma unroll
+    for (int s = 0; s < WS; s++) {
+        if (act[s]) {
+            float4 o = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+            if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+            KN_FOR_EACH_DEST(peers, Y, pmask, yb) *reinterpret_cast<float4 *>(yb + yrow * ldy + n0 + s * 128) = o;
+        }
+    }
+}
+
 template <int NB, bool RELU>
 __global__ void __launch_bounds__(kWarps * 32)
 spmm_lanes_nnz_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -162,6 +237,19 @@ int launch_rowwarp(const int64_t *indptr, const int32_t *indices, const float *d
     return KN_OK;
 }
 
+template <int WS>
+int launch_rowwarp_wide(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
+                        const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, const int32_t *out_rows, cudaStream_t s)
+{
+    const int64_t gx = kn_cdiv(n_rows, kWarps), gy = kn_cdiv(n_vecs, 128 * WS);
+    KN_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large (rows=%lld, n_vecs=%lld)", (long long)n_rows, (long long)n_vecs);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (relu) spmm_rowwarp_wide_kernel<WS, true><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
+    else      spmm_rowwarp_wide_kernel<WS, false><<<grid, kWarps * 32, 0, s>>>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, out_rows, kn_current_peers());
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
 template <int NB>
 int launch_lanes(const int64_t *indptr, const int32_t *indices, const float *data, int64_t n_rows,
                  const float *X, int64_t ldx, float *Y, int64_t ldy, int n_vecs, bool relu, const int32_t *out_rows, cudaStream_t s)
@@ -197,6 +285,12 @@ static int spmm_csr_impl(const int64_t *indptr, const int32_t *indices, const fl
         return launch_lanes<8>(indptr, indices, data, n_rows, X, ldx, Y, ldy, nv, relu, out_rows, s);
     }
     const uintptr_t align = (uintptr_t)X | (uintptr_t)Y;
+    static const int wide = getenv("KN_CSR_WIDE") ? atoi(getenv("KN_CSR_WIDE")) : 2;
+    if (n_vecs % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (align & 15) == 0 && n_vecs >= 2048 && wide > 1) {
+        // enough batch columns to fill the machine with 512-column warps (kn_cdiv(n_rows, 8) x n_vecs / 512 CTAs)
+        if (wide == 2) return launch_rowwarp_wide<2>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
+        return launch_rowwarp_wide<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
+    }
     if (n_vecs % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (align & 15) == 0 && n_vecs >= 128)
         return launch_rowwarp<4>(indptr, indices, data, n_rows, X, ldx, Y, ldy, n_vecs, relu, out_rows, s);
     if (n_vecs % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && (align & 7) == 0 && n_vecs >= 64)

@@ -478,6 +478,16 @@ def tensor_cores_enabled(flag=None):
     return _TC['enabled']
 
 
+_CLUSTERS = [True]
+
+
+def clusters_enabled(flag=None):
+    """Switch the clustered small-group kernel on / off (A/B measurements and tests); returns the current setting."""
+    if flag is not None:
+        _CLUSTERS[0] = bool(flag)
+    return _CLUSTERS[0]
+
+
 def _dedup_value_blocks(cols, vals, group_k, ng, G, K_pad, chunk_bytes=1 << 30):
     """Store identical value blocks once (the reference's unique tiles, keynet/sparse.py:553-568,690-779).
 
@@ -549,8 +559,10 @@ class PatternGroups(object):
         self.padded_values = 0
 
     @staticmethod
-    def build(W, min_group=4, max_pad_waste=0.25, dedup=True):
-        """max_pad_waste: a class is split when a group's K falls below this fraction of the class maximum."""
+    def build(W, min_group=4, max_pad_waste=0.25, dedup=True, hint=None):
+        """max_pad_waste: a class is split when a group's K falls below this fraction of the class maximum.
+        hint: optional int64 CUDA tensor [n_rows], a spatial cluster id per row (rows of neighbouring output pixels share
+        an id, < 0 = none): classes of small groups (G <= 16) are then also stored clustered (csrc/pgcluster.cu)."""
         L = _native.lib()
         dev = W._data.device
         (R, C) = W.shape
@@ -596,6 +608,14 @@ class PatternGroups(object):
             for (b0, b1) in zip(bounds[:-1], bounds[1:]):
                 g_sub = gi[b0:b1]
                 g_sub = g_sub[torch.argsort(first_col[g_sub])]       # neighbouring CTAs gather neighbouring X rows
+                cid = None
+                if hint is not None and int(G) <= PatternGroups.CG_MAX_G:
+                    cid = hint[leader[g_sub]]
+                    if bool((cid >= 0).all()):
+                        o2 = torch.argsort(cid, stable=True)         # groups stored cluster by cluster
+                        (g_sub, cid) = (g_sub[o2], cid[o2])
+                    else:
+                        cid = None
                 K_pad = int((Kl[b0] + 31) // 32 * 32)
                 ng = int(g_sub.numel())
                 pos = (start[g_sub].reshape(-1, 1) + torch.arange(G, device=dev).reshape(1, -1)).reshape(-1)
@@ -618,6 +638,8 @@ class PatternGroups(object):
                     maps = ctypes.create_string_buffer(4 * 128)
                     check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * int(G), int(G), K_pad, maps))
                     cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
+                if cid is not None and int(G) <= PatternGroups.CG_KERNEL_MAX_G and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
+                    cls['cg'] = PatternGroups._cluster(cls, cid, C)
                 pg.classes.append(cls)
                 in_group[rows64] = True
                 pg.grouped_rows += ng * int(G)
@@ -635,12 +657,53 @@ class PatternGroups(object):
             return None
         return pg
 
+    CG_MAX_G = 16            # groups up to this height are ordered by their spatial hint (L1 / L2 locality of the gathers)
+    CG_KERNEL_MAX_G = 8      # ... and run on the clustered kernel when the reduction is short: there the product is bound by
+    CG_KERNEL_MAX_K = 32     # L2 -> SM gather traffic (measured: LeNet conv1 0.48 -> 0.38 ms; conv2 G=16 K=55 is FMA-bound: pg_small)
+    CG_MAX_UNION = 224       # KN_CG_MAX_UNION: rows of the staged tile (224 x 512 B = 112 KB, two CTAs per SM)
+    CG_MAX_BYTES = 256 << 20
+
+    @staticmethod
+    def _cluster(cls, cid, n_cols):
+        """Clustered form of a class of small groups (kn_spmm_cg_f32): union column list per cluster, per-group byte
+        offsets into the staged tile, k-major value blocks.  cid: sorted int64 cluster id of every group."""
+        (G, K_pad, ng) = (cls['G'], cls['K_pad'], cls['n_groups'])
+        dev = cid.device
+        GM = (G + 1) // 2 * 2
+        n_blocks = cls['n_blocks']
+        if (n_blocks * K_pad * GM + ng * K_pad) * 4 > PatternGroups.CG_MAX_BYTES:
+            return None
+        (ucid, cl_of_group) = torch.unique_consecutive(cid, return_inverse=True)
+        n_cl = int(ucid.numel())
+        cols = cls['cols'].reshape(ng, K_pad).to(torch.int64)
+        key = cl_of_group.reshape(-1, 1) * int(n_cols) + cols                       # (cluster, column), row-major
+        (uniq, inv) = torch.unique(key.reshape(-1), sorted=True, return_inverse=True)
+        ucl = uniq // int(n_cols)
+        cl_uptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        cl_uptr[1:] = torch.cumsum(torch.bincount(ucl, minlength=n_cl), 0)
+        u_max = int((cl_uptr[1:] - cl_uptr[:-1]).max())
+        cl_gcount = torch.bincount(cl_of_group, minlength=n_cl)
+        g_max = int(cl_gcount.max())
+        if u_max * 512 + g_max * K_pad * 4 > PatternGroups.CG_MAX_UNION * 512:
+            return None
+        lidx = ((inv.reshape(ng, K_pad) - cl_uptr[cl_of_group].reshape(-1, 1)) * 512).to(torch.int32).contiguous()
+        cl_gptr = torch.zeros(n_cl + 1, dtype=torch.int64, device=dev)
+        cl_gptr[1:] = torch.cumsum(cl_gcount, 0)
+        vT = torch.zeros((n_blocks, K_pad, GM), dtype=torch.float32, device=dev)
+        vT[:, :, :G] = cls['vals'].reshape(n_blocks, G, K_pad).permute(0, 2, 1)
+        return dict(n_clusters=n_cl, u_max=u_max, g_max=g_max, cl_gptr=cl_gptr.to(torch.int32), cl_uptr=cl_uptr.to(torch.int32), ucols=(uniq % int(n_cols)).to(torch.int32),
+                    lidx=lidx, valsT=vT.contiguous())
+
     def spmm(self, x, y, relu):
         L = _native.lib()
         N = x.shape[1]
         flags = _native.KN_SPMM_RELU if relu else 0
         for c in self.classes:
-            if c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
+            cg = c.get('cg')
+            if cg is not None and clusters_enabled():
+                check(L.kn_spmm_cg_f32(ptr(cg['cl_gptr']), ptr(cg['cl_uptr']), ptr(cg['ucols']), ptr(c['rows']), ptr(cg['lidx']), ptr(cg['valsT']), ptr(c['group_k']), ptr(c['block_of']),
+                                       cg['n_clusters'], c['G'], c['K_pad'], cg['u_max'], cg['g_max'], ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+            elif c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
                 check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
                                           ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
             else:
@@ -816,8 +879,42 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_gr
         # pattern groups come from the STRUCTURAL matrix (exact zeros kept): every output pixel keeps its full
         # M-row group even where the reference's offset rounding turned a tiny weight into a dropped zero
         S = SparseMatrix(((n, Kp), *_keycompile(csr0, n, K, A, Ainv, dev, row_scale_slice=sel, keep_zeros=True)), device=dev)
-        W._pg = PatternGroups.build(S)
+        hint = _pixel_tile_hint(ids, n, (M, U // stride, V // stride), C, P, stride, False, dev) if M <= PatternGroups.CG_MAX_G else None
+        W._pg = PatternGroups.build(S, hint=hint)
     return W
+
+
+def _pixel_tile_hint(ids, n, outshape, C, k, stride, depthwise, dev, tile=None):
+    """Spatial cluster id of every compiled row: rows whose underlying Toeplitz row lies in the same t x t tile of output
+    pixels (and, for pooling, the same channel) share an id.  t is the largest tile whose union of taps fits the staging
+    buffer of the clustered kernel; None if not even one pixel does.  ids: Toeplitz row of every compiled row (None = identity)."""
+    (M, Uo, Vo) = outshape
+    K_pad = ((k * k * (1 if depthwise else C) + 1) + 31) // 32 * 32
+    # staged bytes of a t x t tile: union rows x 512 B + one lidx row (K_pad ints) per group
+    staged = lambda t: (((t - 1) * stride + k) ** 2 * (1 if depthwise else C) + 1) * 512 + t * t * K_pad * 4
+    if tile is None:
+        t = 0
+        while t < max(Uo, Vo) and staged(t + 1) <= PatternGroups.CG_MAX_UNION * 512:
+            t += 1
+        if t == 0:
+            return None
+        t = min(t, max(Uo, Vo))
+        for d in range(t, max(1, t // 2), -1):          # prefer a tile that divides the image (equal clusters)
+            if Uo % d == 0 and Vo % d == 0:
+                t = d
+                break
+        tile = (t, t)
+    (th, tw) = tile
+    src = ids if ids is not None else torch.arange(n, dtype=torch.int64, device=dev)
+    px = src % (Uo * Vo)
+    ch = src // (Uo * Vo)
+    (py, pxx) = (px // Vo, px % Vo)
+    nt = -(-Vo // tw)
+    hint = (py // th) * nt + (pxx // tw)
+    if depthwise:
+        hint = ch * (nt * -(-Uo // th)) + hint
+    n_ids = (M if depthwise else 1) * nt * -(-Uo // th)
+    return torch.where(src < M * Uo * Vo, hint, torch.full_like(hint, n_ids))        # homogeneous row: a cluster of its own
 
 
 def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
@@ -839,7 +936,24 @@ def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, c
     (Ainv, Kp) = _remapped(Ainv, col_remap, n_cols_phys)
     csr = _toeplitz_rows(desc, wq, None, ids, n, dev)
     csr = _keycompile(csr, n, K, A, Ainv, dev, row_scale_slice=sel)
-    return SparseMatrix(((n, Kp), *csr), device=dev)
+    W = SparseMatrix(((n, Kp), *csr), device=dev)
+    if W.nnz() >= 4096 and os.environ.get('KN_POOL_ORDER', '1') == '1':
+        # every pooling row has its own column set (one channel): no pattern groups.  Rows of neighbouring pixels of a
+        # channel still share taps, so the CSR kernel walks them in (channel, pixel tile) order -- the 8 rows of a CTA then
+        # hit each other's X rows in L1 whatever permutation the keys apply.
+        hint = _pixel_tile_hint(ids, n, (C, U // stride, V // stride), C, k, stride, True, dev, tile=(2, 4))
+        order = torch.argsort(hint, stable=True)
+        (indptr, indices, data) = csr
+        csr2 = _two_phase(
+            n,
+            lambda row_nnz: check(_native.lib().kn_csr_gather_rows_count(ptr(indptr), ptr(order), n, ptr(row_nnz), stream_ptr())),
+            lambda ip, ix, dt: check(_native.lib().kn_csr_gather_rows_fill(ptr(indptr), ptr(indices), ptr(data), ptr(order), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+            dev)
+        pg = PatternGroups()
+        pg.shape = W.shape
+        pg.rest = dict(n=n, indptr=csr2[0], indices=csr2[1], data=csr2[2], out_rows=order.to(torch.int32))
+        W._pg = pg
+    return W
 
 
 def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
