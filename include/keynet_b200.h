@@ -76,6 +76,21 @@ int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const fl
                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
                          uint32_t flags, void *stream);
 
+/* ---- general key compile: C = A . B on CSR (csrc/spgemm.cu) ------------------------------------------------
+ * Replaces the two scipy csr_matmat calls of `A.dot(W).dot(Ainv)` (keynet/layer.py:35,59,70) for keys with several
+ * entries per row: Givens-rotation orthogonal and doubly stochastic blocks (keynet/sparse.py:288-353), their
+ * block-diagonal repeats (keynet/system.py:398-410).  Three steps, the caller scans in between (kn_exclusive_scan_i64):
+ *   kn_spgemm_bound  ub[r] = number of products a_rj * b_jc of row r                       -> scan -> tmp_ptr
+ *   kn_spgemm_rows   products of row r expanded into tmp[tmp_ptr[r] ..), sorted by column, duplicates added in fp32,
+ *                    exact zeros dropped (scipy never stores one), compacted; row_nnz[r] = kept     -> scan -> out_indptr
+ *   kn_csr_compact   tmp slices -> out CSR (canonical: ascending columns) */
+int kn_spgemm_bound(const int64_t *a_indptr, const int32_t *a_indices, int64_t n_rows, const int64_t *b_indptr, int64_t *ub, void *stream);
+int kn_spgemm_rows(const int64_t *a_indptr, const int32_t *a_indices, const float *a_data, int64_t n_rows,
+                   const int64_t *b_indptr, const int32_t *b_indices, const float *b_data,
+                   const int64_t *tmp_ptr, int32_t *tmp_indices, float *tmp_data, int64_t *row_nnz, void *stream);
+int kn_csr_compact(const int64_t *tmp_ptr, const int32_t *tmp_indices, const float *tmp_data, int64_t n_rows,
+                   const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
+
 /* ---- pattern-grouped execution format (csrc/pgroup.cu) ------------------------------------------
  * B200 form of the reference's unique-tile storage (TiledMatrix / Conv2dTiledMatrix,
  * keynet/sparse.py:517-835): rows with an identical column set form a group whose values are a dense

@@ -88,3 +88,34 @@ __device__ __forceinline__ KnRaster kn_raster(int64_t linear, int64_t n_items, i
     }
     return r;
 }
+
+// normalised bitonic sort of n (key,val) pairs by key, ascending; works for any n >= 0
+template <typename KeyPtr, typename ValPtr>
+__device__ __forceinline__ void bitonic_sort_pairs(KeyPtr keys, ValPtr vals, int n) {
+    if (n < 2) return;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+        // first step of the stage: partner is the mirror inside the k-block
+        for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+            const int blk = i / (k / 2), off = i - blk * (k / 2);
+            const int a = blk * k + off, b = blk * k + (k - 1 - off);
+            if (b < n) {
+                const int32_t ka = keys[a], kb = keys[b];
+                if (ka > kb) { keys[a] = kb; keys[b] = ka; const float t = vals[a]; vals[a] = vals[b]; vals[b] = t; }
+            }
+        }
+        __syncthreads();
+        for (int j = k / 4; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                const int a = 2 * j * (i / j) + (i % j), b = a + j;
+                if (b < n) {
+                    const int32_t ka = keys[a], kb = keys[b];
+                    if (ka > kb) { keys[a] = kb; keys[b] = ka; const float t = vals[a]; vals[a] = vals[b]; vals[b] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+

@@ -1,7 +1,7 @@
 """Serialisation of compiled keynets.  The reference pickles whole Python objects including scipy
 matrices (`vipy.util.save((sensor, knet), 'x.pkl')`, test/test_keynet.py:106, demo/challenge.ipynb); here a keyed
 network is a flat dict of tensors -- canonical CSR per layer (int64 indptr, int32 indices, fp32 data), layer names and
-flags, sensor keys as (perm, scale) -- written with torch.save, so it loads without this package's classes being
+flags, sensor keys as (perm, scale[, bias]) or CSR for general keys -- written with torch.save, so it loads without this package's classes being
 picklable and without recompiling any key."""
 from collections import OrderedDict
 
@@ -11,17 +11,28 @@ from torch import nn
 
 from . import layer as _layer
 from . import system as _system
-from .sparse import SparseMatrix, MonomialKey
+from .sparse import SparseMatrix, MonomialKey, SparseKey
 
 FORMAT_VERSION = 1
 
 
 def _key_state(K):
-    return None if K is None else {'perm': torch.from_numpy(K.perm), 'scale': torch.from_numpy(K.scale)}
+    if K is None:
+        return None
+    if isinstance(K, SparseKey):          # general key: CSR
+        return {'indptr': torch.from_numpy(K.indptr), 'indices': torch.from_numpy(K.indices), 'data': torch.from_numpy(K.data.astype(np.float32)), 'shape': tuple(K.shape)}
+    st = {'perm': torch.from_numpy(K.perm), 'scale': torch.from_numpy(K.scale)}
+    if K.bias is not None:
+        st['bias'] = torch.from_numpy(K.bias)
+    return st
 
 
 def _key_load(s):
-    return None if s is None else MonomialKey(s['perm'].numpy(), s['scale'].numpy())
+    if s is None:
+        return None
+    if 'indptr' in s:
+        return SparseKey(s['indptr'].numpy(), s['indices'].numpy(), s['data'].numpy(), tuple(s['shape']))
+    return MonomialKey(s['perm'].numpy(), s['scale'].numpy(), s['bias'].numpy() if 'bias' in s else None)
 
 
 def state_dict(sensor, knet):

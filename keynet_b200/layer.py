@@ -8,7 +8,7 @@ from torch import nn
 
 from . import sparse
 from .globals import verbose
-from .sparse import SparseMatrix, MonomialKey
+from .sparse import SparseMatrix, MonomialKey, SparseKey
 
 
 class FusedReLU(nn.Module):
@@ -35,9 +35,16 @@ class KeyedLayer(nn.Module):
         self._tileshape = tileshape
         self._fused_relu = False
         self._rows = rows
-        assert A is None or isinstance(A, MonomialKey), 'general (non-monomial) keys are a later scope row (SURVEY.md 8f-2)'
-        assert isinstance(Ainv, MonomialKey), 'general (non-monomial) keys are a later scope row (SURVEY.md 8f-2)'
+        assert A is None or isinstance(A, (MonomialKey, SparseKey)), 'A must be a key (MonomialKey / SparseKey)'
+        assert isinstance(Ainv, (MonomialKey, SparseKey)), 'Ainv must be a key (MonomialKey / SparseKey)'
         t0 = time.time()
+        if isinstance(A, SparseKey) or isinstance(Ainv, SparseKey):
+            # general keys (Givens-orthogonal / doubly stochastic blocks, keynet/system.py:398-410): the un-keyed layer matrix,
+            # then the two products of keynet/layer.py:35,46,59,70 as GPU SpGEMMs (csrc/spgemm.cu)
+            assert rows is None and col_remap is None, 'row-sharded compile supports monomial keys'
+            self._init_general(module, inshape, outshape, A, Ainv)
+            self._finish(module, inshape, outshape, tileshape, keep_csr, t0)
+            return
 
         if isinstance(module, nn.Conv2d):
             assert len(module.kernel_size) == 1 or len(module.kernel_size) == 2 and (module.kernel_size[0] == module.kernel_size[1]), "Kernel must be square"
@@ -78,6 +85,38 @@ class KeyedLayer(nn.Module):
         else:
             raise ValueError('unsupported layer type "%s"' % str(type(module)))
 
+        self._finish(module, inshape, outshape, tileshape, keep_csr, t0)
+
+    def _init_general(self, module, inshape, outshape, A, Ainv):
+        if isinstance(module, nn.Conv2d):
+            assert module.kernel_size[0] == module.kernel_size[1], "Kernel must be square"
+            assert module.stride[0] == module.stride[1], "Strides must be isotropic"
+            assert module.padding[0] == module.kernel_size[0] // 2 and module.padding[1] == module.kernel_size[1] // 2, "Padding is assumed to be equal to (kernelsize-1)/2"
+            stride = module.stride[0]
+            self._repr = 'Conv2d: in_channels=%d, out_channels=%d, kernel_size=%s, stride=%s' % (module.in_channels, module.out_channels, str(module.kernel_size), str(stride))
+            bias = module.bias.detach().cpu().numpy() if module.bias is not None else np.zeros(module.out_channels, dtype=np.float32)
+            W = sparse.keyed_toeplitz_conv2d(inshape, module.weight.detach().cpu().numpy(), bias, stride, None, MonomialKey(np.arange(int(np.prod(inshape)) + 1)), build_groups=False)
+        elif isinstance(module, nn.AvgPool2d):
+            stride = module.stride if isinstance(module.stride, int) else module.stride[0]
+            kernel_size = module.kernel_size if isinstance(module.kernel_size, int) else module.kernel_size[0]
+            self._repr = 'AvgPool2d: kernel_size=%s, stride=%s' % (str(kernel_size), str(stride))
+            W = sparse.keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, None, MonomialKey(np.arange(int(np.prod(inshape)) + 1)))
+            W._pg = None
+        elif isinstance(module, nn.Linear):
+            self._repr = 'Linear: in_features=%d, out_features=%d' % (module.in_features, module.out_features)
+            n = module.in_features + 1
+            W = sparse.keyed_linear(module.weight.detach(), module.bias.detach() if module.bias is not None else None, None, MonomialKey(np.arange(n)))
+        elif isinstance(module, nn.ReLU):
+            self._repr = 'ReLU'
+            self.W = SparseMatrix(SparseKey.coerce(A).dot(SparseKey.coerce(Ainv)).astype(np.float32))
+            return
+        else:
+            raise ValueError('unsupported layer type "%s"' % str(type(module)))
+        if A is not None:
+            W = A.dot(W)                  # left product first, like A.dot(W).dot(Ainv)
+        self.W = W.matmul(Ainv)
+
+    def _finish(self, module, inshape, outshape, tileshape, keep_csr, t0):
         if tileshape is None:
             self.W.optimize()          # pattern-grouped execution format for batched forward (no-op if the builder made it)
         if tileshape is not None:

@@ -85,6 +85,8 @@ class MonomialKey(object):
             return MonomialKey(other.perm[self.perm], (self.scale * other.scale[self.perm]).astype(np.float32), bias)
         if isinstance(other, SparseMatrix):
             return other._left_monomial(self)
+        if isinstance(other, SparseKey):
+            return SparseKey.from_monomial(self).dot(other)
         raise TypeError('cannot multiply MonomialKey with %s' % str(type(other)))
 
     def transpose(self):
@@ -127,8 +129,129 @@ class MonomialKey(object):
         return A.asformat(format)
 
 
+class SparseKey(object):
+    """General sparse key on the host: CSR with ascending columns (numpy).  The reference's key families with several
+    entries per row -- Givens-rotation orthogonal blocks, doubly stochastic blocks and their dense inverses, and any
+    product of those with monomial / affine keys (keynet/sparse.py:238-353, keynet/system.py:382-410,467-468).
+    Key algebra stays on the host like the reference's (keys have O(n) .. O(n * blocksize) entries); the compile of a
+    layer matrix with such a key is the GPU SpGEMM of csrc/spgemm.cu."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int64)
+        self.data = np.ascontiguousarray(data)
+        assert self.data.dtype in (np.float32, np.float64)
+        self.shape = (int(shape[0]), int(shape[1]))
+        assert len(self.indptr) == self.shape[0] + 1 and len(self.indices) == len(self.data) == self.indptr[-1]
+        self.ndim = 2
+        self.bias = None          # a bias column is an ordinary column here
+
+    dtype = property(lambda self: self.data.dtype)
+    nnz = property(lambda self: int(len(self.data)))
+
+    def __repr__(self):
+        return '<keynet_b200.SparseKey: shape=%s, nnz=%d, dtype=%s>' % (str(self.shape), self.nnz, str(self.data.dtype))
+
+    def has_bias(self):
+        return False
+
+    def is_identity(self):
+        n = self.shape[0]
+        return self.shape[0] == self.shape[1] and self.nnz == n and bool(np.array_equal(self.indices, np.arange(n))) and bool(np.all(self.data == 1))
+
+    # -- constructors
+    @staticmethod
+    def from_coo(rows, cols, vals, shape, sum_duplicates=True, drop_zeros=True):
+        """Canonical CSR from triplets: duplicates added in the given order, exact zeros dropped (scipy csr_matmat / tocsr)."""
+        rows = np.asarray(rows, dtype=np.int64); cols = np.asarray(cols, dtype=np.int64); vals = np.asarray(vals)
+        order = np.lexsort((cols, rows))                     # stable: equal (row, col) keep their input order
+        (rows, cols, vals) = (rows[order], cols[order], vals[order])
+        if len(rows) and sum_duplicates:
+            head = np.ones(len(rows), dtype=bool)
+            head[1:] = (rows[1:] != rows[:-1]) | (cols[1:] != cols[:-1])
+            starts = np.nonzero(head)[0]
+            if len(starts) != len(rows):
+                vals = np.add.reduceat(vals, starts)
+                (rows, cols) = (rows[starts], cols[starts])
+        if drop_zeros and len(vals):
+            keep = vals != 0
+            (rows, cols, vals) = (rows[keep], cols[keep], vals[keep])
+        indptr = np.zeros(shape[0] + 1, dtype=np.int64)
+        np.add.at(indptr, rows + 1, 1)
+        return SparseKey(np.cumsum(indptr), cols, vals, shape)
+
+    @staticmethod
+    def from_monomial(K):
+        n = K.shape[0]
+        if K.bias is None:
+            return SparseKey(np.arange(n + 1), K.perm, K.scale, K.shape)
+        nz = np.nonzero(K.bias)[0]
+        return SparseKey.from_coo(np.concatenate([np.arange(n), nz]), np.concatenate([K.perm, np.full(len(nz), n - 1)]),
+                                  np.concatenate([K.scale, K.bias[nz]]), K.shape, sum_duplicates=True, drop_zeros=False)
+
+    @staticmethod
+    def from_dense(D):
+        (r, c) = np.nonzero(D)
+        return SparseKey.from_coo(r, c, np.asarray(D)[r, c], D.shape, sum_duplicates=False)
+
+    @staticmethod
+    def coerce(K):
+        return K if isinstance(K, SparseKey) else SparseKey.from_monomial(K)
+
+    # -- algebra
+    def rows(self):
+        return np.repeat(np.arange(self.shape[0]), np.diff(self.indptr))
+
+    def dot(self, other):
+        """self . other: SparseKey / MonomialKey -> SparseKey (host, expand-sort-compress like csr_matmat: products in the
+        common dtype, duplicates added in expansion order, exact zeros dropped); SparseMatrix -> SparseMatrix (GPU SpGEMM)."""
+        if isinstance(other, SparseMatrix):
+            return other._left_general(self)
+        b = SparseKey.coerce(other)
+        assert self.shape[1] == b.shape[0], 'non-conformal keys %s, %s' % (str(self.shape), str(b.shape))
+        dt = np.result_type(self.data.dtype, b.data.dtype)
+        blen = np.diff(b.indptr)[self.indices]                           # products per entry of self
+        tot = int(blen.sum())
+        off = np.concatenate([[0], np.cumsum(blen)])[:-1]
+        idx = np.arange(tot, dtype=np.int64) - np.repeat(off, blen) + np.repeat(b.indptr[self.indices], blen)
+        vals = np.repeat(self.data.astype(dt), blen) * b.data.astype(dt)[idx]
+        return SparseKey.from_coo(np.repeat(self.rows(), blen), b.indices[idx], vals, (self.shape[0], b.shape[1]))
+
+    def transpose(self):
+        return SparseKey.from_coo(self.indices, self.rows(), self.data, (self.shape[1], self.shape[0]), sum_duplicates=False, drop_zeros=False)
+
+    T = property(lambda self: self.transpose())
+
+    def astype(self, dtype):
+        return SparseKey(self.indptr, self.indices, self.data.astype(dtype), self.shape)
+
+    def diagonal(self):
+        d = np.zeros(min(self.shape), dtype=self.data.dtype)
+        r = self.rows()
+        on = (r == self.indices) & (r < len(d))
+        d[r[on]] = self.data[on]
+        return d
+
+    def block(self, r0, r1, c0, c1):
+        """Sub-matrix [r0:r1, c0:c1] (scipy slicing)."""
+        r = self.rows()
+        keep = (r >= r0) & (r < r1) & (self.indices >= c0) & (self.indices < c1)
+        return SparseKey.from_coo(r[keep] - r0, self.indices[keep] - c0, self.data[keep], (r1 - r0, c1 - c0), sum_duplicates=False, drop_zeros=False)
+
+    # -- interop (tests, visualisation); not used by the product path
+    def todense(self):
+        D = np.zeros(self.shape, dtype=self.data.dtype)
+        D[self.rows(), self.indices] = self.data
+        return D
+
+    def toscipy(self, format='csr'):
+        import scipy.sparse
+        return scipy.sparse.csr_matrix((self.data, self.indices.astype(np.int32), self.indptr), shape=self.shape).asformat(format)
+
+
 def is_key(A):
-    return isinstance(A, MonomialKey)
+    return isinstance(A, (MonomialKey, SparseKey))
+
 
 
 def sparse_identity_matrix(n, dtype=np.float32):
@@ -175,7 +298,8 @@ def sparse_channelorder_to_blockorder_matrix(shape, blocksize, withinverse=True)
         warnings.warn('[keynet_b200.sparse.sparse_channelorder_to_blockorder]:  Ragged blockorder for blocksize=%d and shape=%s' % (blocksize, str(shape)))
     (H_pad, W_pad) = (int(blocksize * np.ceil(H / float(blocksize))), int(blocksize * np.ceil(W / float(blocksize))))
     order = blockview(np.arange(H_pad * W_pad).reshape(H_pad, W_pad), blocksize).flatten()[0:H * W]
-    if H_pad != H or W_pad != W:
+    if (H_pad != H or W_pad != W) and not np.array_equal(np.sort(order), np.arange(H * W)):
+        # (the reference truncates the padded block order; for Cx1x1 activations that is the identity, otherwise not a permutation)
         raise ValueError('ragged block order (blocksize=%d, shape=%s) is not a permutation' % (blocksize, str(shape)))
     perm = np.concatenate([order + c * H * W for c in range(C)])
     A = MonomialKey(perm)
@@ -185,6 +309,15 @@ def sparse_channelorder_to_blockorder_matrix(shape, blocksize, withinverse=True)
 def sparse_affine_to_linear(A, bias=None, dtype=np.float32):
     """[A 0; 0 1]: homogeneous augmentation of a key (keynet/sparse.py:87-96).  Keys with a bias
     column are not monomial and belong to the general-key path."""
+    if isinstance(A, SparseKey):
+        n = A.shape[0]
+        (rows, cols, vals) = (A.rows(), A.indices, A.data)
+        if bias is not None:
+            bias = np.asarray(bias).reshape(-1)
+            nz = np.nonzero(bias)[0]
+            (rows, cols, vals) = (np.concatenate([rows, nz]), np.concatenate([cols, np.full(len(nz), n)]), np.concatenate([vals, bias[nz].astype(vals.dtype)]))
+        (rows, cols, vals) = (np.concatenate([rows, [n]]), np.concatenate([cols, [n]]), np.concatenate([vals, np.ones(1, dtype=vals.dtype)]))
+        return SparseKey.from_coo(rows, cols, vals, (n + 1, n + 1), sum_duplicates=False, drop_zeros=False)
     assert isinstance(A, MonomialKey), 'sparse_affine_to_linear expects a key matrix'
     n = A.shape[0]
     b = None
@@ -213,10 +346,90 @@ def diagonal_affine_to_linear(A, bias=None, withinverse=False, dtype=np.float32)
     return (L, MonomialKey(np.arange(n + 1), np.concatenate([inv, [1.0]]).astype(np.float32), np.concatenate([binv, [0.0]]).astype(np.float32)))
 
 
+def sparse_orthogonal_matrix(n, k_iter, balanced=True, withinverse=False, dtype=np.float32):
+    """Product of k_iter random Givens rotations S = G_k ... G_1 (keynet/sparse.py:288-309), same numpy RNG draws as the
+    reference: one rand() for the angle per rotation, one permutation(n) whenever the index pool runs low.  Rows are
+    kept sparse in float64 (a rotation rewrites two rows), rounded to `dtype` at the end; the inverse is the transpose."""
+    assert n >= 2
+    assert balanced, 'only the balanced construction is used by keygen (keynet/system.py:385,406)'
+    rows = {}                                    # row -> {col: float64}; rows never touched are identity rows
+    G_index = []
+    for k in range(0, int(k_iter)):
+        theta = np.random.rand() * 2 * np.pi
+        G_index = np.random.permutation(range(0, n)).tolist() + G_index if len(G_index) <= 1 else G_index
+        (i, j) = (G_index.pop(), G_index.pop())
+        (c, sn) = (np.cos(theta), np.sin(theta))
+        (Si, Sj) = (rows.get(i, {i: 1.0}), rows.get(j, {j: 1.0}))
+        (ni, nj) = ({}, {})
+        for col in set(Si) | set(Sj):
+            (a, b) = (Si.get(col), Sj.get(col))
+            # row i of G = (c at i, -sin at j), row j = (sin at i, c at j); csr_matmat adds the products of a row in column
+            # order of G -- two terms, so the order does not matter -- and never stores an exact zero
+            vi = (c * a if a is not None else 0.0) + (-sn * b if b is not None else 0.0) if (a is not None and b is not None) else (c * a if a is not None else -sn * b)
+            vj = (sn * a if a is not None else 0.0) + (c * b if b is not None else 0.0) if (a is not None and b is not None) else (sn * a if a is not None else c * b)
+            if vi != 0:
+                ni[col] = vi
+            if vj != 0:
+                nj[col] = vj
+        (rows[i], rows[j]) = (ni, nj)
+    (r, cidx, v) = ([], [], [])
+    for (row, d) in rows.items():
+        for (col, val) in d.items():
+            r.append(row); cidx.append(col); v.append(val)
+    untouched = np.setdiff1d(np.arange(n), np.fromiter(rows.keys(), dtype=np.int64, count=len(rows)))
+    S = SparseKey.from_coo(np.concatenate([np.asarray(r, dtype=np.int64), untouched]), np.concatenate([np.asarray(cidx, dtype=np.int64), untouched]),
+                           np.concatenate([np.asarray(v, dtype=np.float64), np.ones(len(untouched))]), (n, n), sum_duplicates=False, drop_zeros=False).astype(dtype)
+    return S if not withinverse else (S, S.transpose())
+
+
+def sparse_random_diagonally_dominant_doubly_stochastic_matrix(n, k, n_iter=100, withinverse=False):
+    """Doubly stochastic band matrix with k diagonals made diagonally dominant, Sinkhorn-normalised and conjugated by two
+    random permutations; inverse by dense inversion (keynet/sparse.py:335-353).  Same RNG draws as the reference
+    (rand(k, n), then the left and the right permutation).  Evaluated densely in float64 -- the block is at most
+    blocksize^2 x blocksize^2 -- and returned as float64 SparseKeys like the reference's."""
+    n_iter = 10 if k <= 3 else n_iter
+    d = np.random.rand(k, n)
+    d[0, :] = np.maximum(d[0, :], np.sum(d[1:, :], axis=0) + 0.1)
+    d = d / np.sum(d, axis=0).reshape(1, n)
+    k_range = list(range(-((k - 1) // 2), 1 + ((k - 1) // 2)) if k % 2 == 1 else list(range(-(k // 2), k // 2)))
+    k_range.remove(0)
+    k_range = [0] + k_range
+    A = np.zeros((n, n), dtype=np.float64)
+    for (row, off) in enumerate(k_range):                       # scipy.sparse.spdiags: data[row, j] sits at A[j - off, j]
+        j = np.arange(max(0, off), min(n, n + off))
+        A[j - off, j] = d[row, j]
+    for it in range(0, n_iter):
+        nrm = np.abs(A).sum(axis=0); nrm[nrm == 0] = 1.0
+        A = A / nrm.reshape(1, n)                               # sklearn normalize(norm='l1', axis=0)
+        nrm = np.abs(A).sum(axis=1); nrm[nrm == 0] = 1.0
+        A = A / nrm.reshape(n, 1)
+    P1 = sparse_permutation_matrix(n)
+    P2 = sparse_permutation_matrix(n)
+    B = np.zeros_like(A)
+    B[:, P2.perm] = A[P1.perm, :]                               # P1 . A . P2
+    if not withinverse:
+        return SparseKey.from_dense(B)
+    return (SparseKey.from_dense(B), SparseKey.from_dense(np.linalg.inv(B)))
+
+
 def sparse_block_diagonal_repeat(B, shape):
     """Key B repeated down the diagonal of an (N,N) matrix, truncated at N (the monomial case of the
     reference's DiagonalTiledMatrix / sparse_block_diagonal, keynet/sparse.py:215-235,657-687)."""
-    assert isinstance(B, MonomialKey) and shape[0] == shape[1]
+    assert shape[0] == shape[1]
+    if isinstance(B, SparseKey):
+        (n, h) = (int(shape[0]), B.shape[0])
+        if h > n:
+            B = B.block(0, n, 0, n)                       # keynet/sparse.py:662-663
+            h = n
+        reps = n // h
+        (r, c, v) = (B.rows(), B.indices, B.data)
+        rows = (np.tile(r, reps) + np.repeat(np.arange(reps) * h, len(r)))
+        cols = (np.tile(c, reps) + np.repeat(np.arange(reps) * h, len(r)))
+        vals = np.tile(v, reps)
+        tail = np.arange(reps * h, n)                     # ragged tail tile is the identity (sparse.py:680-681)
+        return SparseKey.from_coo(np.concatenate([rows, tail]), np.concatenate([cols, tail]), np.concatenate([vals, np.ones(len(tail), dtype=v.dtype)]),
+                                  (n, n), sum_duplicates=False, drop_zeros=False)
+    assert isinstance(B, MonomialKey)
     (n, h) = (int(shape[0]), B.shape[0])
     reps = int(np.ceil(n / float(h)))
     perm = (np.tile(B.perm, reps) + np.repeat(np.arange(reps) * h, h))[0:n]
@@ -257,6 +470,32 @@ def _two_phase(n_rows, count, fill, device):
     return (indptr, indices, data)
 
 
+def _spgemm_device(a, n_rows, b):
+    """C = A . B on the GPU (csrc/spgemm.cu).  a, b: (indptr int64, indices int32, data f32) CUDA tensors (indptr may be a
+    row-slice view with a non-zero base).  Returns canonical CSR (ascending columns, exact zeros dropped)."""
+    L = _native.lib()
+    (a_ip, a_ix, a_dt) = a
+    (b_ip, b_ix, b_dt) = b
+    dev = a_dt.device
+    tmp_ptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    if n_rows > 0:
+        check(L.kn_spgemm_bound(ptr(a_ip), ptr(a_ix), n_rows, ptr(b_ip), ptr(tmp_ptr[1:]), stream_ptr()))
+    _scan_counts_inplace(tmp_ptr)
+    total = int(tmp_ptr[-1].item())
+    tmp_ix = torch.empty(total, dtype=torch.int32, device=dev)
+    tmp_dt = torch.empty(total, dtype=torch.float32, device=dev)
+    out_ip = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    if n_rows > 0:
+        check(L.kn_spgemm_rows(ptr(a_ip), ptr(a_ix), ptr(a_dt), n_rows, ptr(b_ip), ptr(b_ix), ptr(b_dt), ptr(tmp_ptr), ptr(tmp_ix), ptr(tmp_dt), ptr(out_ip[1:]), stream_ptr()))
+    _scan_counts_inplace(out_ip)
+    nnz = int(out_ip[-1].item())
+    out_ix = torch.empty(nnz, dtype=torch.int32, device=dev)
+    out_dt = torch.empty(nnz, dtype=torch.float32, device=dev)
+    if n_rows > 0 and nnz > 0:
+        check(L.kn_csr_compact(ptr(tmp_ptr), ptr(tmp_ix), ptr(tmp_dt), n_rows, ptr(out_ip), ptr(out_ix), ptr(out_dt), stream_ptr()))
+    return (out_ip, out_ix, out_dt)
+
+
 class SparseMatrix(object):
     """Device-resident CSR matrix implementing the reference's SparseMatrix operator protocol
     (keynet/sparse.py:419-514): torchdot / dot / matmul / nnz / transpose / tocoo / tocsr /
@@ -291,6 +530,11 @@ class SparseMatrix(object):
             self._indptr = torch.from_numpy(indptr.astype(np.int64)).to(dev)
             self._indices = torch.from_numpy(indices).to(dev)
             self._data = torch.from_numpy(data).to(dev)
+        elif isinstance(A, SparseKey):
+            self.shape = A.shape
+            self._indptr = torch.from_numpy(A.indptr).to(dev)
+            self._indices = torch.from_numpy(A.indices.astype(np.int32)).to(dev)
+            self._data = torch.from_numpy(A.data.astype(np.float32)).to(dev)
         elif isinstance(A, tuple) and len(A) == 4:
             (shape, indptr, indices, data) = A
             self.shape = (int(shape[0]), int(shape[1]))
@@ -382,13 +626,29 @@ class SparseMatrix(object):
     def matmul(self, A):
         """In-place self <- self . A for a monomial key A (column reindex + scale + zero drop + sort),
         the right-hand SpGEMM of keynet/layer.py:35 / keynet/sparse.py:472-480."""
+        if isinstance(A, (SparseKey, SparseMatrix)):
+            # general right factor: GPU SpGEMM (csrc/spgemm.cu)
+            B = A if isinstance(A, SparseMatrix) else SparseMatrix(A, device=self._data.device)
+            assert self.shape[1] == B.shape[0]
+            (self._indptr, self._indices, self._data) = _spgemm_device((self._indptr, self._indices, self._data), self.shape[0], (B._indptr, B._indices, B._data))
+            self.shape = (self.shape[0], B.shape[1])
+            self._pg = None
+            return self
         if not isinstance(A, MonomialKey):
-            raise NotImplementedError('matmul with a general sparse matrix is a later scope row (SURVEY.md 8f-2)')
+            raise TypeError('matmul expects a key or a SparseMatrix, got %s' % str(type(A)))
         assert self.shape[1] == A.shape[0]
         (self._indptr, self._indices, self._data) = _keycompile((self._indptr, self._indices, self._data), self.shape[0], self.shape[1],
                                                                 None, A, self._data.device)
         self.shape = (self.shape[0], A.shape[1])
         return self
+
+    def _left_general(self, A):
+        """A . self for a general sparse key A (GPU SpGEMM): the left product of keynet/layer.py:35."""
+        assert A.shape[1] == self.shape[0]
+        dev = self._data.device
+        K = SparseMatrix(A, device=dev)
+        csr = _spgemm_device((K._indptr, K._indices, K._data), A.shape[0], (self._indptr, self._indices, self._data))
+        return SparseMatrix(((A.shape[0], self.shape[1]), *csr), device=dev)
 
     def _left_monomial(self, A):
         """A . self for a monomial key A: row gather + row scale + zero drop."""

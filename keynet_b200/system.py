@@ -17,7 +17,7 @@ from . import torch as _ktorch
 from . import util as _util
 from .blockpermute import hierarchical_block_permutation_matrix
 from .globals import verbose
-from .sparse import (MonomialKey, diagonal_affine_to_linear, sparse_permutation_matrix, sparse_identity_matrix, sparse_uniform_random_diagonal_matrix,
+from .sparse import (MonomialKey, SparseKey, sparse_orthogonal_matrix, sparse_random_diagonally_dominant_doubly_stochastic_matrix, diagonal_affine_to_linear, sparse_permutation_matrix, sparse_identity_matrix, sparse_uniform_random_diagonal_matrix,
                      sparse_channelorder_to_blockorder_matrix, sparse_channelorder_to_pixelorder_matrix, sparse_affine_to_linear,
                      sparse_block_diagonal_repeat)
 
@@ -275,13 +275,12 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
 
     RNG draws happen in the reference's order: global geometric, local geometric, global photometric, local
     photometric.  All photometric options are supported (gain keys are monomial; bias / affine keys are monomial
-    plus a bias column, a family closed under products).  Givens-orthogonal and doubly-stochastic geometric keys need a
-    general sparse key compile and raise NotImplementedError for now."""
+    plus a bias column, a family closed under products).  Givens-orthogonal and doubly-stochastic geometric keys are general
+    sparse keys (sparse.SparseKey): composed on the host like the reference's, compiled into the layers by the GPU SpGEMM."""
     allowable_memoryorder = set(['channel', 'block'])
     allowable_global_geometric = set(['identity', 'permutation', 'hierarchical_permutation', 'hierarchical_rotation', 'givens_orthogonal'])
     allowable_local_geometric = set(['identity', 'permutation', 'doubly_stochastic', 'givens_orthogonal'])
     allowable_photometric = set(['identity', 'uniform_random_gain', 'uniform_random_affine', 'uniform_random_bias', 'constant_bias', 'linear_bias', 'blockwise_constant_bias'])
-    general = 'is not a monomial key: general key compile is a later scope row (SURVEY.md 8f-2)'
 
     (channels, height, width) = shape
     N = int(np.prod(shape))
@@ -327,7 +326,9 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
         if memoryorder != 'channel':
             (G, Ginv) = (c.dot(G).dot(cinv), c.dot(Ginv).dot(cinv))
     elif global_geometric == 'givens_orthogonal':
-        raise NotImplementedError("global_geometric='givens_orthogonal' " + general)
+        assert alpha is not None
+        assert tileshape is None, "Global givens rotation orthogonal matrix is not tile compressible"
+        (G, Ginv) = sparse_orthogonal_matrix(N, int(alpha), balanced=True, withinverse=True)
     else:
         raise ValueError("Invalid global geometric transform '%s' - must be in '%s'" % (global_geometric, str(allowable_global_geometric)))
     (G, Ginv) = (sparse_affine_to_linear(G), sparse_affine_to_linear(Ginv))
@@ -338,8 +339,20 @@ def keygen(shape, global_geometric, local_geometric, global_photometric, local_p
         assert blocksize is not None and height == width
         g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(sparse_permutation_matrix(blocknumel), (H, H)), (N, N))   # spatial, then channel repeat
         ginv = g.transpose()
-    elif local_geometric in ('doubly_stochastic', 'givens_orthogonal'):
-        raise NotImplementedError("local_geometric='%s' " % local_geometric + general)
+    elif local_geometric == 'doubly_stochastic':
+        assert blocksize is not None and alpha is not None and height == width
+        assert blocksize < 8192, "Blocksize %d must be less than 8192, since doubly_stochastic requires the direct inverse of a dense matrix" % blocksize
+        (g, ginv) = sparse_random_diagonally_dominant_doubly_stochastic_matrix(blocknumel, int(alpha), withinverse=True)
+        # the reference carries these blocks (and every matrix compiled with them) in float64; this path is fp32 throughout
+        g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(g.astype(np.float32), (H, H)), (N, N))        # spatial, then channel repeat
+        ginv = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(ginv.astype(np.float32), (H, H)), (N, N))
+    elif local_geometric == 'givens_orthogonal':
+        assert alpha is not None and blocksize is not None and height == width
+        (g, ginv) = sparse_orthogonal_matrix(blocknumel, int(alpha), balanced=True, withinverse=True)
+        (Pb, Pbinv) = sparse_permutation_matrix(blocknumel, withinverse=True)
+        (g, ginv) = (Pb.dot(g), ginv.dot(Pbinv))
+        g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(g, (H, H)), (N, N))                             # spatial, then channel repeat
+        ginv = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(ginv, (H, H)), (N, N))
     else:
         raise ValueError("Invalid local geometric transform '%s' - must be in '%s'" % (local_geometric, str(allowable_local_geometric)))
     (g, ginv) = (sparse_affine_to_linear(g), sparse_affine_to_linear(ginv))

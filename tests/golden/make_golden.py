@@ -278,6 +278,27 @@ def g_lenet_cfg3():
     save('lenet_cfg3.npz', d)
 
 
+def g_lenet_givens():
+    """General (non-monomial) keys: the reference's own LeNet orthogonal configuration (test/test_keynet.py:180-197):
+    Givens-rotation local keys + affine photometric keys + hierarchical rotation, block memory order."""
+    d = {}
+    net = numpy_weights(keynet.mnist.LeNet_AvgPool(), 11).eval()
+
+    def make(net):
+        np.random.seed(0)
+        return keynet.system.Keynet((1, 28, 28), net, tileshape=None,
+                                    global_geometric='hierarchical_rotation', hierarchical_blockshape=(2, 2), hierarchical_permute_at_level=(0),
+                                    global_photometric='uniform_random_bias',
+                                    local_geometric='givens_orthogonal', alpha=2.0, blocksize=8,
+                                    local_photometric='uniform_random_affine', beta=1.0, gamma=1.0,
+                                    memoryorder='block')
+    (sensor, knet) = _record_keynet(d, net, (1, 28, 28), make, N=2)
+    d['num_parameters'] = np.array(knet.num_parameters())
+    for k in [k for k in d if k.startswith('keygen.')]:          # the sensor key pins the RNG stream; the rest is redundant
+        del d[k]
+    save('lenet_givens.npz', d)
+
+
 def g_challenge():
     import pickle
     import PIL.Image
@@ -415,7 +436,7 @@ def g_tiled():
 
 
 ALL = dict(toeplitz=g_toeplitz, keygen=g_keygen, blockpermute=g_blockpermute, lenet_cfg1=g_lenet_cfg1, lenet_cfg3=g_lenet_cfg3,
-           challenge=g_challenge, acn_cfg2=g_acn_cfg2, vggtwin=g_vggtwin, tiled=g_tiled)
+           challenge=g_challenge, lenet_givens=g_lenet_givens, acn_cfg2=g_acn_cfg2, vggtwin=g_vggtwin, tiled=g_tiled)
 
 if __name__ == '__main__':
     which = sys.argv[1:] or list(ALL.keys())
