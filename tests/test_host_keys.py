@@ -50,11 +50,17 @@ def test_keygen_bias_keys_match_reference(name):
     assert np.allclose(I, np.eye(I.shape[0]), atol=1e-5)
 
 
-def test_keygen_general_geometric_keys_are_refused_loudly():
-    with pytest.raises(NotImplementedError):
-        system.keygen((1, 8, 8), 'givens_orthogonal', 'identity', 'identity', 'identity', alpha=2)
-    with pytest.raises(NotImplementedError):
-        system.keygen((1, 8, 8), 'identity', 'doubly_stochastic', 'identity', 'identity', alpha=2, blocksize=4)
+def test_keygen_general_geometric_keys_are_inverse_pairs():
+    """Givens-orthogonal / doubly stochastic options give general sparse keys (sparse.SparseKey) with A . Ainv = I."""
+    from keynet_b200.sparse import SparseKey
+    for kw in [dict(global_geometric='givens_orthogonal', alpha=9), dict(local_geometric='doubly_stochastic', alpha=2, blocksize=4),
+               dict(local_geometric='givens_orthogonal', alpha=3, blocksize=4, local_photometric='uniform_random_affine', beta=1.0, gamma=1.0)]:
+        args = dict(global_geometric='identity', local_geometric='identity', global_photometric='identity', local_photometric='identity')
+        args.update(kw)
+        np.random.seed(4)
+        (A, Ainv) = system.keygen((2, 8, 8), **args)
+        assert isinstance(A, SparseKey) and A.shape == (129, 129)
+        assert np.allclose(A.todense().astype(np.float64) @ Ainv.todense().astype(np.float64), np.eye(129), atol=1e-4)
 
 
 def test_keygen_rejects_unknown_options():
