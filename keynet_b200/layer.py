@@ -147,6 +147,10 @@ class KeyedLayer(nn.Module):
             Ainv = SparseMatrix(Ainv)
         return Ainv.torchdot(x_affine.t()).t()
 
+    def spy(self, mindim=256, showdim=1024, range=None):
+        """Picture of the keyed layer matrix (keynet/layer.py:104-106)."""
+        return self.W.spy(mindim, showdim, range)
+
     def nnz(self):
         assert self.W is not None, "Layer not keyed"
         return self.W.nnz()

@@ -89,6 +89,14 @@ class MonomialKey(object):
             return SparseKey.from_monomial(self).dot(other)
         raise TypeError('cannot multiply MonomialKey with %s' % str(type(other)))
 
+    def apply(self, X):
+        """self . X for a dense host array X [n, m] (image-side plumbing: mat2gray keys, keynet/system.py:176-197)."""
+        X = np.asarray(X)
+        Y = self.scale.reshape(-1, 1).astype(X.dtype) * X[self.perm]
+        if self.bias is not None:
+            Y = Y + self.bias.reshape(-1, 1).astype(X.dtype) * X[-1:, :]
+        return Y
+
     def transpose(self):
         assert self.bias is None, 'a key with a bias column has no monomial transpose (use the inverse from the generator)'
         n = len(self.perm)
@@ -217,6 +225,13 @@ class SparseKey(object):
         vals = np.repeat(self.data.astype(dt), blen) * b.data.astype(dt)[idx]
         return SparseKey.from_coo(np.repeat(self.rows(), blen), b.indices[idx], vals, (self.shape[0], b.shape[1]))
 
+    def apply(self, X):
+        """self . X for a dense host array X [n, m]."""
+        X = np.asarray(X)
+        Y = np.zeros((self.shape[0], X.shape[1]), dtype=np.result_type(self.data.dtype, X.dtype))
+        np.add.at(Y, self.rows(), self.data.reshape(-1, 1) * X[self.indices])
+        return Y
+
     def transpose(self):
         return SparseKey.from_coo(self.indices, self.rows(), self.data, (self.shape[1], self.shape[0]), sum_duplicates=False, drop_zeros=False)
 
@@ -344,6 +359,59 @@ def diagonal_affine_to_linear(A, bias=None, withinverse=False, dtype=np.float32)
     b = np.asarray(bias, dtype=np.float64).reshape(-1)
     binv = 0.0 - (inv * b * 2.0) / 2.0          # (Ainv u)(v Ainv) / (1 + v Ainv u): the factors of two are exact
     return (L, MonomialKey(np.arange(n + 1), np.concatenate([inv, [1.0]]).astype(np.float32), np.concatenate([binv, [0.0]]).astype(np.float32)))
+
+
+def mat2gray(x, dtype=np.float32):
+    """Affine key pair mapping the values of x onto [0, 1]: xh = x / (max - min) - min / (max - min) (keynet/sparse.py:25-33)."""
+    x = np.asarray(x)
+    (xmin, xmax) = (np.min(x), np.max(x))
+    gain = 1.0 / (xmax - xmin)
+    bias = -xmin / (xmax - xmin)
+    n = int(np.max(x.shape))
+    return diagonal_affine_to_linear(MonomialKey(np.arange(n), np.full(n, gain, dtype=np.float64).astype(np.float32)), np.ones((n, 1)) * bias, withinverse=True, dtype=dtype)
+
+
+def _jet(v):
+    """v in [0, 1] -> uint8 RGB with the classic jet ramp."""
+    v = np.clip(v, 0.0, 1.0)
+    rgb = np.stack([np.clip(1.5 - np.abs(4 * v - 3), 0, 1), np.clip(1.5 - np.abs(4 * v - 2), 0, 1), np.clip(1.5 - np.abs(4 * v - 1), 0, 1)], axis=-1)
+    return (255 * rgb).astype(np.uint8)
+
+
+def spy(A, mindim=256, showdim=1024, range=None, eps=None):
+    """Picture of the sparsity / values of A (a key, a SparseMatrix or anything with tocoo()): the block
+    A[range[0]:range[1], range[0]:range[1]] binned to about mindim x mindim cells (cell = mean of its stored values), min-max
+    normalised, jet-coloured and enlarged to showdim with nearest-neighbour interpolation (keynet/sparse.py:382-415).
+    Returns a PIL image (the reference returns a vipy image)."""
+    from PIL import Image
+    if isinstance(A, MonomialKey):
+        A = SparseKey.from_monomial(A)
+    if isinstance(A, SparseKey):
+        (shape, row, col, val) = (A.shape, A.rows(), A.indices, A.data.astype(np.float32))
+    else:
+        C = A.tocoo()
+        (shape, row, col, val) = (tuple(C.shape), np.asarray(C.row, dtype=np.int64), np.asarray(C.col, dtype=np.int64), np.asarray(C.data, dtype=np.float32))
+    if range is not None:
+        assert isinstance(range, tuple) and len(range) == 2, "Range must be tuple (start_dim, end_dim)"
+        (i, j) = range
+        keep = (row >= i) & (row < j) & (col >= i) & (col < j)
+        (row, col, val, shape) = (row[keep] - i, col[keep] - i, val[keep], (j - i, j - i))
+    if eps is not None:
+        keep = np.abs(val) > eps
+        (row, col, val) = (row[keep], col[keep], val[keep])
+    scale = float(mindim) / min(shape)
+    n = 1.0 if scale >= 1 else 1.0 / scale
+    (H, W) = (int(np.ceil(shape[0] / n)) + (0 if scale >= 1 else 1), int(np.ceil(shape[1] / n)) + (0 if scale >= 1 else 1))
+    (bi, bj) = ((row // n).astype(np.int64), (col // n).astype(np.int64))
+    (acc, cnt) = (np.zeros(H * W, dtype=np.float64), np.zeros(H * W, dtype=np.float64))
+    np.add.at(acc, bi * W + bj, val)
+    np.add.at(cnt, bi * W + bj, 1.0)
+    img = (acc / np.maximum(cnt, 1.0)).reshape(H, W).astype(np.float32)
+    (lo, hi) = (float(img.min()), float(img.max()))
+    img = (img - lo) / (hi - lo) if hi > lo else np.zeros_like(img)
+    im = Image.fromarray(_jet(img), 'RGB')
+    f = float(showdim) / max(im.size)
+    return im.resize((max(1, int(round(im.size[0] * f))), max(1, int(round(im.size[1] * f)))), Image.NEAREST)
 
 
 def sparse_orthogonal_matrix(n, k_iter, balanced=True, withinverse=False, dtype=np.float32):
@@ -687,6 +755,10 @@ class SparseMatrix(object):
     def csr_arrays(self):
         """(indptr int64, indices int32, data float32) as numpy arrays on the host (canonical: sorted columns)."""
         return (self._indptr.cpu().numpy(), self._indices.cpu().numpy(), self._data.cpu().numpy())
+
+    def spy(self, mindim=256, showdim=1024, range=None, eps=None):
+        """PIL picture of the matrix (keynet/sparse.py:460-462)."""
+        return spy(self, mindim, showdim, range, eps)
 
     def tocoo(self):
         import scipy.sparse

@@ -229,8 +229,68 @@ class KeyedSensor(_layer.KeyedLayer):
             self._tensor = _ktorch.linear_to_affine(x_raw, (N,) + tuple(self._inshape[1:]))
         return self
 
+    # ---- image-side I/O (keynet/system.py:173-235; PIL images where the reference uses vipy) -------------------
+    def _from_pil(self, im):
+        (C, H, W) = self._inshape[1:]
+        im = im.convert('L' if C == 1 else 'RGB')
+        a = np.asarray(im, dtype=np.float32)
+        a = a[:, :, None] if a.ndim == 2 else a
+        self._tensor = torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).unsqueeze(0)     # HxWxC [0,255] -> 1xCxHxW
+        return self
+
     def load(self, imgfile, imagekey=None):
-        raise NotImplementedError('image file I/O is outside the keyed-layer path (SURVEY.md 8f-3); use fromtensor()')
+        """Load an image file as the sensor's 1xCxHxW tensor (values 0..255, resized to the sensor shape); with
+        `imagekey` (returned by save()) the file is an encrypted image and is decrypted while loading."""
+        from PIL import Image
+        im = Image.open(imgfile)
+        (C, H, W) = self._inshape[1:]
+        if imagekey is not None:
+            self._from_pil(im)
+            assert tuple(self._tensor.shape) == tuple(self._inshape), 'encrypted image must have the sensor shape'
+            x_linear = _ktorch.affine_to_linear((1.0 / 255.0) * self._tensor)                          # [0,255] -> [0,1]
+            x = imagekey.apply(x_linear.numpy().transpose())                                            # DecryptKey . mat2gray^-1
+            self._tensor = _ktorch.linear_to_affine(torch.as_tensor(np.ascontiguousarray(x.transpose()), dtype=torch.float32), self._inshape)
+        else:
+            self._from_pil(im.resize((W, H), Image.BILINEAR))
+        self._im = im
+        return self
+
+    def fromimage(self, im):
+        """im: PIL image with the sensor's height / width."""
+        assert (im.size[1], im.size[0]) == tuple(self._inshape[2:]), 'image must have the sensor shape'
+        self._im = im
+        return self._from_pil(im)
+
+    def save(self, outfile='/tmp/out.png'):
+        """Write the ENCRYPTED image as an 8-bit PNG (values min-max normalised by a mat2gray key) and return
+        (outfile, imagekey); load(outfile, imagekey) decrypts it again (to 8-bit quantisation)."""
+        from PIL import Image
+        assert self.isencrypted() and self._tensor.shape[0] == 1
+        x_linear = self._tensor.detach().cpu().numpy().transpose()                                      # (D+1) x 1
+        (A, Ainv) = _sparse.mat2gray(x_linear.flatten()[:-1])
+        x = _ktorch.linear_to_affine(torch.as_tensor(np.ascontiguousarray(A.apply(x_linear).transpose()), dtype=torch.float32), self._inshape)
+        a = np.clip(np.rint(255.0 * x[0].numpy().transpose(1, 2, 0)), 0, 255).astype(np.uint8)       # 1xCxHxW [0,1] -> HxWxC uint8
+        Image.fromarray(a[:, :, 0] if a.shape[2] == 1 else a).save(outfile)
+        return (outfile, self._decryptkey.dot(Ainv))
+
+    def asimage(self):
+        """The current tensor (encrypted or not) as a min-max normalised uint8 PIL image."""
+        from PIL import Image
+        x = self._tensor
+        if self.isencrypted():
+            x = _ktorch.linear_to_affine(x[0:1].cpu(), self._inshape)
+        a = x[0] if x.ndim == 4 else x
+        a = a.detach().cpu().numpy().transpose(1, 2, 0).astype(np.float32)
+        (lo, hi) = (float(a.min()), float(a.max()))
+        a = np.uint8(255 * (a - lo) / (hi - lo)) if hi > lo else np.zeros(a.shape, dtype=np.uint8)
+        return Image.fromarray(a[:, :, 0] if a.shape[2] == 1 else a)
+
+    def toimage(self):
+        return self.asimage()
+
+    def show(self):
+        self.asimage().show()
+        return self
 
 
 class PublicKeyedSensor(KeyedSensor):

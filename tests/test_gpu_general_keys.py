@@ -116,3 +116,39 @@ def test_tiled_orthogonal_keynet_factory():
     y = knet.forward(sensor.fromtensor(x).encrypt().astensor()).reshape(8, -1).numpy()
     yp = net(x).detach().numpy()
     assert np.allclose(y, yp, atol=1e-3), np.abs(y - yp).max()
+
+
+def test_sensor_image_roundtrip_through_png(tmp_path):
+    """KeyedSensor.load -> encrypt -> save (8-bit PNG of the encrypted image + image key) -> load(imagekey) recovers the
+    image to quantisation (keynet/system.py:173-207, README quickstart with demo/owl.jpg)."""
+    from PIL import Image
+    from keynet_b200 import system
+    rs = np.random.RandomState(0)
+    src = tmp_path / 'in.png'
+    Image.fromarray(rs.randint(0, 255, size=(28, 28)).astype(np.uint8)).save(src)
+    np.random.seed(0)
+    (sensor, _) = system.Keynet((1, 28, 28), None, global_geometric='permutation', global_photometric='uniform_random_gain', beta=1.0)
+    x = sensor.load(str(src)).tensor().clone()
+    assert x.shape == (1, 1, 28, 28) and float(x.max()) <= 255
+    (outfile, imagekey) = sensor.encrypt().save(str(tmp_path / 'enc.png'))
+    enc = np.asarray(Image.open(outfile))
+    assert enc.shape == (28, 28) and not np.array_equal(enc, np.asarray(Image.open(src)))
+    assert sensor.asimage().size == (28, 28)
+    y = sensor.load(outfile, imagekey).tensor()
+    step = float(sensor_range(x, sensor)) / 255.0
+    assert np.abs(y.numpy() - x.numpy()).max() <= 2.0 * step + 1e-3
+
+
+def sensor_range(x, sensor):
+    """Dynamic range of the encrypted image (gain keys in [1, 2)): quantisation step of the PNG, seen after decryption."""
+    return 2.0 * float(x.max() - x.min()) + 1.0
+
+
+def test_layer_spy_picture():
+    from keynet_b200 import system, nets
+    torch.manual_seed(0)
+    np.random.seed(0)
+    (sensor, knet) = system.PermutationKeynet((1, 28, 28), nets.LeNet_AvgPool().eval())
+    L = dict(knet.keyedlayers())['conv1']
+    im = L.spy(mindim=128, showdim=256)
+    assert im.mode == 'RGB' and max(im.size) == 256

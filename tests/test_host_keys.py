@@ -125,3 +125,23 @@ def test_find_closest_positive_divisor_and_blockview():
     assert util.find_closest_positive_divisor(7, 2) == 7
     A = np.arange(36).reshape(6, 6)
     assert np.array_equal(util.blockview(A, 3)[1, 0], A[3:6, 0:3])
+
+
+def test_mat2gray_key_maps_onto_unit_interval_and_inverts():
+    rs = np.random.RandomState(2)
+    x = (rs.randn(40) * 7 + 3).astype(np.float32)
+    (A, Ainv) = sparse.mat2gray(x)
+    xl = np.concatenate([x, [1.0]]).reshape(-1, 1).astype(np.float32)
+    y = A.apply(xl)
+    assert abs(float(y[:-1].min())) < 1e-6 and abs(float(y[:-1].max()) - 1.0) < 1e-6 and y[-1, 0] == 1.0
+    assert np.allclose(Ainv.apply(y), xl, atol=1e-4)
+    K = sparse.SparseKey.from_monomial(A)
+    assert np.allclose(K.apply(xl), y, atol=1e-6)
+
+
+def test_spy_renders_keys_and_blocks():
+    P = sparse.sparse_permutation_matrix(300)
+    im = sparse.spy(P, mindim=64, showdim=128)
+    assert im.mode == 'RGB' and max(im.size) == 128
+    im2 = sparse.spy(sparse.SparseKey.from_monomial(P), mindim=512, showdim=256, range=(0, 100), eps=0.5)
+    assert max(im2.size) == 256
