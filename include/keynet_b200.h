@@ -211,6 +211,12 @@ int kn_csr_gather_rows_fill(const int64_t *indptr, const int32_t *indices, const
  * affine_to_linear (keynet/torch.py:65-68) fused with the transpose the reference does at
  * layer.py:92: images [n_vecs][dim] row-major -> X [dim+1][ldx] with a trailing row of ones. */
 int kn_affine_to_linear_t(const float *images, int64_t n_vecs, int64_t dim, float *X, int64_t ldx, void *stream);
+/* KeyedSensor.encrypt (keynet/system.py:250-255) in one pass for a monomial image key A (one entry per row: permutation x
+ * gain, optionally a bias column): Y = A . affine_to_linear(images)^T written directly, Y[row_of_col[d]][n] =
+ * scale_of_col[d] * images[n][d] (+ row_bias[row], NULL = none); d = dim is the homogeneous 1.  Saves the pass that
+ * kn_affine_to_linear_t + kn_spmm_csr_f32 spend writing and re-reading the un-keyed X. */
+int kn_encrypt_monomial_t(const float *images, int64_t n_vecs, int64_t dim, const int32_t *row_of_col, const float *scale_of_col,
+                          const float *row_bias, float *Y, int64_t ldy, void *stream);
 /* inverse: X [dim+1][ldx] -> out [n_vecs][dim]; *bad_count_dev (int32, device) receives the number of
  * vectors whose homogeneous coordinate is not within atol of 1 (linear_to_affine raises on it, torch.py:74). */
 int kn_linear_to_affine_t(const float *X, int64_t ldx, int64_t n_vecs, int64_t dim, float *out,

@@ -20,7 +20,7 @@ SYMBOLS = [
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
     'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
-    'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact',
+    'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact', 'kn_encrypt_monomial_t',
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
         'kn_spmm_pg_f32': [vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_spmm_cg_f32': [vp, vp, vp, vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_debug_tc_timing': [ctypes.c_int32, vp],
+        'kn_encrypt_monomial_t': [vp, i64, i64, vp, vp, vp, vp, i64, vp],
         'kn_spgemm_bound': [vp, vp, i64, vp, vp, vp],
         'kn_spgemm_rows': [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
         'kn_csr_compact': [vp, vp, vp, i64, vp, vp, vp, vp],

@@ -28,11 +28,12 @@ class ForwardPlan(object):
         self.K = self.layers[-1][1].shape[0] - 1
         N = self.N
         self.images = torch.empty((N, self.D), dtype=torch.float32, device=self.dev)
-        self.X0 = torch.empty((self.D + 1, N), dtype=torch.float32, device=self.dev)
         self.acts = [torch.empty((W.shape[0], N), dtype=torch.float32, device=self.dev) for (_, W, _) in self.layers]
         self.logits = torch.empty((N, self.K), dtype=torch.float32, device=self.dev)
         self.bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.launches_per_run = 2 + sum((W._pg.launches() if (W._pg is not None and N >= 32 and N % 4 == 0) else 1) for (_, W, _) in self.layers)
+        from .sparse import MonomialKey
+        self.fused_encrypt = isinstance(sensor.keypair()[0], MonomialKey)          # image key applied inside the transpose kernel
+        self.launches_per_run = (1 if self.fused_encrypt else 3) + sum((W._pg.launches() if (W._pg is not None and N >= 32 and N % 4 == 0) else 1) for (_, W, _) in self.layers[1:])
         self.time_layers = time_layers
         # per-layer CUDA events on the launch stream, one set per timed step (read back after the timed region)
         self.layer_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.layers]
@@ -42,16 +43,18 @@ class ForwardPlan(object):
         if use_graph and not time_layers:
             self._capture()
 
-    # ---- the chain: 1 layout kernel + one SpMM per keyed layer + 1 layout kernel
+    # ---- the chain: encrypt kernel + one SpMM per keyed layer + 1 layout kernel
     def _chain(self):
         L = _native.lib()
         s = _native.stream_ptr()
-        _native.check(L.kn_affine_to_linear_t(_native.ptr(self.images), self.N, self.D, _native.ptr(self.X0), self.N, s))
-        x = self.X0
+        x = None
         for (i, (name, W, relu)) in enumerate(self.layers):
             if self.time_layers:
                 self.layer_events[self.event_set][i][0].record()
-            spmm(W, x, relu=relu, out=self.acts[i])
+            if i == 0:
+                self.sensor.encrypt_into(self.images, self.acts[0])     # homogenise + transpose + image key (one kernel for monomial keys)
+            else:
+                spmm(W, x, relu=relu, out=self.acts[i])
             if self.time_layers:
                 self.layer_events[self.event_set][i][1].record()
             x = self.acts[i]

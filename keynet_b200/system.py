@@ -172,6 +172,28 @@ class KeyedSensor(_layer.KeyedLayer):
         self._layertype = 'input'
         self._fused_relu = False
         self._repr = 'KeyedSensor'
+        self._enc = None
+
+    def encrypt_into(self, images, Y):
+        """Y[D+1][N] = A . affine_to_linear(images[N][D])^T on the current stream.  A monomial image key (permutation x gain
+        [+ bias column]) is applied while the batch is transposed (kn_encrypt_monomial_t, one pass); a general key takes the
+        two-pass route (homogenise + transpose, then the CSR SpMM)."""
+        (N, D) = (int(images.shape[0]), int(np.prod(images.shape[1:])))
+        assert tuple(Y.shape) == (D + 1, N) and Y.is_contiguous() and images.is_contiguous()
+        K = self._encryptkey
+        if isinstance(K, MonomialKey) and K.shape[0] == D + 1 and (K.bias is None or K.perm[-1] == D):
+            if self._enc is None:
+                dev = Y.device
+                row_of_col = np.empty(D + 1, dtype=np.int32); row_of_col[K.perm] = np.arange(D + 1, dtype=np.int32)
+                scale_of_col = np.empty(D + 1, dtype=np.float32); scale_of_col[K.perm] = K.scale
+                self._enc = (torch.from_numpy(row_of_col).to(dev), torch.from_numpy(scale_of_col).to(dev), None if K.bias is None else torch.from_numpy(K.bias).to(dev))
+            (rc, sc, rb) = self._enc
+            _native.check(_native.lib().kn_encrypt_monomial_t(_native.ptr(images), N, D, _native.ptr(rc), _native.ptr(sc), _native.ptr(rb), _native.ptr(Y), N, _native.stream_ptr()))
+            return 1
+        X = torch.empty((D + 1, N), dtype=torch.float32, device=Y.device)
+        _native.check(_native.lib().kn_affine_to_linear_t(_native.ptr(images), N, D, _native.ptr(X), N, _native.stream_ptr()))
+        _sparse.spmm(self.W, X, out=Y)
+        return 2
 
     def __repr__(self):
         return str('<KeyedSensor: height=%d, width=%d, channels=%d>' % (self._inshape[2], self._inshape[3], self._inshape[1]))
@@ -214,9 +236,9 @@ class KeyedSensor(_layer.KeyedLayer):
             dev = torch.device('cuda', torch.cuda.current_device())
             xd = x.to(dev, non_blocking=True).contiguous()
             (N, D) = (xd.shape[0], int(np.prod(xd.shape[1:])))
-            X = torch.empty((D + 1, N), dtype=torch.float32, device=dev)
-            _native.check(_native.lib().kn_affine_to_linear_t(_native.ptr(xd), N, D, _native.ptr(X), N, _native.stream_ptr()))
-            y = _sparse.spmm(self.W, X).t()
+            Y = torch.empty((D + 1, N), dtype=torch.float32, device=dev)
+            self.encrypt_into(xd, Y)
+            y = Y.t()
             self._tensor = y.cpu() if on_host else y
         return self
 
