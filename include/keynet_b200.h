@@ -110,6 +110,11 @@ int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data,
 int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
+/* Split-K epilogue for a layer that is ONE huge group (dense fully connected layers): the K range is cut into S slices
+ * that run as S groups of kn_spmm_pg_tc_f32 / kn_spmm_pg_f32 writing partial rows part[s*G + i][n_vecs]; this adds them:
+ * Y[rows[i]][:] = relu?(sum_s part[s*G + i][:]) (and performs the peer stores of the row-sharded path). */
+int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+
 /* Clustered variant for small groups (G <= 16; csrc/pgcluster.cu): the groups of a tile of neighbouring output pixels
  * form a cluster with ONE union column list that is staged in shared memory once per (cluster, 128 batch columns), so a
  * 3x3 convolution reads every X row from L2 about once instead of 9 times.

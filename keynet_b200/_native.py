@@ -20,7 +20,7 @@ SYMBOLS = [
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
     'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
-    'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact', 'kn_encrypt_monomial_t',
+    'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact', 'kn_encrypt_monomial_t', 'kn_splitk_reduce_f32',
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
         'kn_spmm_cg_f32': [vp, vp, vp, vp, vp, vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, i64, vp, i64, i64, u32, vp],
         'kn_debug_tc_timing': [ctypes.c_int32, vp],
         'kn_encrypt_monomial_t': [vp, i64, i64, vp, vp, vp, vp, i64, vp],
+        'kn_splitk_reduce_f32': [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, i64, i64, u32, vp],
         'kn_spgemm_bound': [vp, vp, i64, vp, vp, vp],
         'kn_spgemm_rows': [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
         'kn_csr_compact': [vp, vp, vp, i64, vp, vp, vp, vp],
@@ -112,11 +113,20 @@ def require_cuda():
         raise NativeError('keynet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
 
 
+_PEERS_STATE = [[], None]
+
+
+def current_output_peers():
+    """(ptrs, row_mask) last passed to set_output_peers by this process."""
+    return (list(_PEERS_STATE[0]), _PEERS_STATE[1])
+
+
 def set_output_peers(ptrs, row_mask=None):
     """Fused all-gather: subsequent spmm launches of this thread write every output row to all `ptrs` (device addresses of
     the same Y slot on every rank); an empty list restores normal stores.  row_mask: uint8 CUDA tensor, one byte per
     output row, bit i = peer i needs the row (None = every row to every peer)."""
     n = len(ptrs)
+    (_PEERS_STATE[0], _PEERS_STATE[1]) = ([int(p) for p in ptrs], row_mask)
     arr = (ctypes.c_uint64 * max(n, 1))(*[int(p) for p in ptrs])
     if row_mask is None:
         check(lib().kn_output_peers(arr, n))

@@ -295,6 +295,31 @@ pg_small_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ co
     }
 }
 
+// split-K epilogue: Y[rows[i]][:] = relu?( sum_s part[s*G + i][:] ).  A layer with one huge pattern group (a dense fully
+// connected layer: VGG16 fc6 is 4096 x 25 089) has too few (row chunk, batch tile) work items to fill 148 SMs, so its K range
+// is cut into S slices that run as S independent groups writing partial rows; this pass adds them (and is where the fused
+// ReLU and the peer stores of the row-sharded path happen).
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads)
+splitk_reduce_kernel(const float *__restrict__ part, int S, int G, const int32_t *__restrict__ rows, float *__restrict__ Y, int64_t ldy, int64_t n_vecs,
+                     const __grid_constant__ KnPeers peers)
+{
+    const int64_t n4 = n_vecs / 4;
+    const int64_t total = (int64_t)G * n4;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = t / n4, c = (t - i * n4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < S; s++) {
+            const float4 v = *reinterpret_cast<const float4 *>(part + ((int64_t)s * G + i) * n_vecs + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (RELU) { acc.x = fmaxf(acc.x, 0.0f); acc.y = fmaxf(acc.y, 0.0f); acc.z = fmaxf(acc.z, 0.0f); acc.w = fmaxf(acc.w, 0.0f); }
+        const int64_t yrow = rows[i];
+        const unsigned pmask = kn_peer_mask(peers, yrow);
+        KN_FOR_EACH_DEST(peers, Y, pmask, yb) *reinterpret_cast<float4 *>(yb + yrow * ldy + c) = acc;
+    }
+}
+
 template <int GM>
 int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int G, int K_pad,
                  const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
@@ -374,6 +399,20 @@ KN_API int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float
     if (n_groups == 0) return KN_OK;
     KN_REQUIRE(indptr && indices && data && rows && cols && vals, "pg_pack: null pointer");
     pg_pack_kernel<<<row_grid(n_groups * G), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, rows, n_groups, G, K_pad, cols, vals);
+    KN_CHECK_LAUNCH();
+    return KN_OK;
+}
+
+KN_API int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+    KN_REQUIRE(S > 0 && G > 0 && n_vecs >= 0 && ldy >= n_vecs, "splitk_reduce: bad shape (S=%d G=%d)", S, G);
+    if (n_vecs == 0) return KN_OK;
+    KN_REQUIRE(part && rows && Y, "splitk_reduce: null pointer");
+    KN_REQUIRE(n_vecs % 4 == 0 && ldy % 4 == 0 && (((uintptr_t)part | (uintptr_t)Y) & 15) == 0, "splitk_reduce: n_vecs, ldy must be multiples of 4 and buffers 16-byte aligned");
+    const int64_t total = (int64_t)G * (n_vecs / 4);
+    const int64_t want = kn_cdiv(total, kThreads), cap = (int64_t)kn_sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (flags & KN_SPMM_RELU) splitk_reduce_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(part, S, G, rows, Y, ldy, n_vecs, kn_current_peers());
+    else                      splitk_reduce_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(part, S, G, rows, Y, ldy, n_vecs, kn_current_peers());
     KN_CHECK_LAUNCH();
     return KN_OK;
 }

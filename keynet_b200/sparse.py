@@ -970,6 +970,8 @@ class PatternGroups(object):
                     maps = ctypes.create_string_buffer(4 * 128)
                     check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * int(G), int(G), K_pad, maps))
                     cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
+                if cls['tc'] is not None and ng == 1 and Kl[b0] >= PatternGroups.SPLITK_MIN_K:
+                    cls['splitk'] = PatternGroups._split_k(cls, int(Kl[b0]))
                 if cid is not None and int(G) <= PatternGroups.CG_KERNEL_MAX_G and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
                     cls['cg'] = PatternGroups._cluster(cls, cid, C)
                 pg.classes.append(cls)
@@ -988,6 +990,33 @@ class PatternGroups(object):
         if len(pg.classes) == 0:
             return None
         return pg
+
+    SPLITK_MAX_BATCH = 1024  # wider batches already give every SM a batch tile
+    SPLITK_MIN_K = 2048      # a single group with a reduction at least this long is cut into K slices (dense fc layers)
+
+    @staticmethod
+    def _split_k(cls, K):
+        """A class that is ONE group (all rows of a dense layer share the column set): S groups over K slices writing partial
+        rows, so that row chunks x S >= the SM count.  Returns the inner class dict (own TF32 planes and TMA descriptors)."""
+        L = _native.lib()
+        (G, K_pad) = (cls['G'], cls['K_pad'])
+        dev = cls['vals'].device
+        chunks = -(-G // 256) if G > 256 else 1                        # row chunks of the tensor-core kernel
+        S = max(2, min(-(-148 // chunks), K // 512))
+        Kp = (-(-K // S) + 31) // 32 * 32
+        S = -(-K // Kp)
+        cols = cls['cols'][:K].to(torch.int64)
+        vals = cls['vals'].reshape(G, K_pad)[:, :K]
+        pad = S * Kp - K
+        cols_s = torch.cat([cols, cols[-1:].expand(pad)]).reshape(S, Kp).to(torch.int32).contiguous()
+        vals_s = torch.cat([vals, torch.zeros((G, pad), dtype=torch.float32, device=dev)], dim=1).reshape(G, S, Kp).permute(1, 0, 2).contiguous().reshape(-1)
+        group_k = torch.tensor([min(Kp, K - s * Kp) for s in range(S)], dtype=torch.int32, device=dev)
+        (vhi, vlo) = (torch.empty_like(vals_s), torch.empty_like(vals_s))
+        check(L.kn_pg_tc_split(ptr(vals_s), vals_s.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
+        maps = ctypes.create_string_buffer(4 * 128)
+        check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), S * G, G, Kp, maps))
+        return dict(S=S, G=G, K_pad=Kp, rows=torch.arange(S * G, dtype=torch.int32, device=dev), cols=cols_s.reshape(-1), group_k=group_k,
+                    tc=dict(hi=vhi, lo=vlo, maps=maps), part={})
 
     CG_MAX_G = 16            # groups up to this height are ordered by their spatial hint (L1 / L2 locality of the gathers)
     CG_KERNEL_MAX_G = 8      # ... and run on the clustered kernel when the reduction is short: there the product is bound by
@@ -1035,6 +1064,19 @@ class PatternGroups(object):
             if cg is not None and clusters_enabled():
                 check(L.kn_spmm_cg_f32(ptr(cg['cl_gptr']), ptr(cg['cl_uptr']), ptr(cg['ucols']), ptr(c['rows']), ptr(cg['lidx']), ptr(cg['valsT']), ptr(c['group_k']), ptr(c['block_of']),
                                        cg['n_clusters'], c['G'], c['K_pad'], cg['u_max'], cg['g_max'], ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+            elif c.get('splitk') is not None and N >= PatternGroups.TC_MIN_BATCH and N <= PatternGroups.SPLITK_MAX_BATCH and tensor_cores_enabled():
+                k = c['splitk']
+                part = k['part'].get(N)
+                if part is None:
+                    part = k['part'][N] = torch.empty((k['S'] * k['G'], N), dtype=torch.float32, device=x.device)
+                saved = _native.current_output_peers()
+                if saved[0]:
+                    _native.set_output_peers([])                      # the partial rows are local scratch
+                check(L.kn_spmm_pg_tc_f32(k['tc']['maps'], ptr(k['rows']), ptr(k['cols']), ptr(k['group_k']), None, k['S'], k['G'], k['K_pad'],
+                                          ptr(x), N, ptr(part), N, N, 0, stream_ptr()))
+                if saved[0]:
+                    _native.set_output_peers(*saved)
+                check(L.kn_splitk_reduce_f32(ptr(part), k['S'], k['G'], ptr(c['rows']), ptr(y), N, N, flags, stream_ptr()))
             elif c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
                 check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
                                           ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
@@ -1047,7 +1089,7 @@ class PatternGroups(object):
                                          ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
 
     def launches(self):
-        return len(self.classes) + (1 if self.rest is not None else 0)
+        return sum(2 if c.get('splitk') is not None else 1 for c in self.classes) + (1 if self.rest is not None else 0)
 
     def summary(self):
         return dict(classes=[(c['G'], c['K_pad'], c['n_groups']) for c in self.classes], unique_blocks=[c['n_blocks'] for c in self.classes], tensor_core=[c['tc'] is not None for c in self.classes], grouped_rows=self.grouped_rows,

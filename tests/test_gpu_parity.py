@@ -614,3 +614,28 @@ def test_photometric_keynets_match_plain_net():
         assert np.allclose(xd.numpy(), x.numpy(), atol=1e-4)
         if 'bias' in kw['global_photometric'] or 'affine' in kw['global_photometric']:
             assert not np.allclose(xc.numpy()[:, :-1], x.reshape(4, -1).numpy(), atol=1e-3)      # the image really is keyed
+
+
+def test_splitk_dense_layer_matches_oracle():
+    """A dense fully connected layer is ONE pattern group; with a long reduction it runs as K slices + a reduce pass
+    (kn_splitk_reduce_f32).  Same result as the oracle, with and without the fused ReLU, at a ragged K."""
+    from keynet_b200 import sparse
+    from keynet_b200.sparse import MonomialKey
+    ko = _ko()
+    rs = np.random.RandomState(0)
+    (n_out, n_in, N) = (300, 5001, 256)
+    Wt = torch.from_numpy(rs.randn(n_out, n_in).astype(np.float32) / 70.0)
+    b = torch.from_numpy(rs.randn(n_out).astype(np.float32))
+    A = MonomialKey(np.concatenate([rs.permutation(n_out), [n_out]]), np.concatenate([rs.rand(n_out) + 0.5, [1.0]]).astype(np.float32))
+    Ainv = MonomialKey(np.concatenate([rs.permutation(n_in), [n_in]]))
+    W = sparse.keyed_linear(Wt, b, A, Ainv)
+    W.optimize()
+    cls = [c for c in W._pg.classes if c.get('splitk') is not None]
+    assert len(cls) == 1 and cls[0]['splitk']['S'] >= 2
+    X = rs.randn(n_in + 1, N).astype(np.float32); X[-1] = 1
+    (ip, ix, dt) = W.csr_arrays()
+    for relu in (False, True):
+        ref = ko.spmm(ko.csr(W.shape, ip, ix, dt), X, relu=relu)
+        y = sparse.spmm(W, torch.from_numpy(X).cuda(), relu=relu).cpu().numpy()
+        assert _close(y, ref), np.abs(y - ref).max()
+        assert np.array_equal(y[-1], np.ones(N, dtype=np.float32))
