@@ -280,6 +280,21 @@ def run_row_sharded(args, rank, world, local_rank):
         step()
         layer_ms = [(type(m._model).__name__ and k, round(a, 3), round(b, 3)) for (k, a, b) in m.layer_times_ms()]
         m.time_layers = False
+    # correctness of the sharded forward, outside the timed region: the decrypted-by-construction logits of the first images
+    # against the plain torch network on the host
+    err = None
+    if rank == 0:
+        import copy
+        plain = copy.deepcopy(wl['net'])
+        for (k, mod) in list(plain.named_children()):      # the pooling the reference actually keys: centred k x k windows,
+            if isinstance(mod, torch.nn.AvgPool2d):        # divisor k*k (keynet/layer.py:48-56 ignores padding / ceil_mode)
+                ks = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
+                st = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
+                setattr(plain, k, torch.nn.AvgPool2d(ks, st, ks // 2, ceil_mode=False, count_include_pad=True))
+        with torch.no_grad():
+            yp = plain(x[:4].cpu()).numpy()
+        yk = y[:4, :-1].cpu().numpy()
+        err = {'max_abs_err_vs_plain_net': float(np.abs(yk - yp).max()), 'max_abs_logit': float(np.abs(yp).max()), 'argmax_equal': bool(np.array_equal(yk.argmax(1), yp.argmax(1)))}
     nnz_local = m.num_parameters_local()
     stats = torch.tensor([ms, float(nnz_local), torch.cuda.max_memory_allocated() / 1e9], device='cuda', dtype=torch.float64)
     if world > 1:
@@ -300,7 +315,7 @@ def run_row_sharded(args, rank, world, local_rank):
                'config': {'workload': wl['label'], 'global_batch': N, 'parallelism': 'rows x%d, %s' % (world, 'fused SpMM+all-gather (NVLink peer stores)' if m.fused else 'NCCL all-gather per layer'),
                           'nnz': int(nnz), 'nnz_max_rank': int(mx[1]), 'key_compile_s': round(t_compile, 3), 'hbm_allocated_gb_max_rank': round(float(mx[2]), 2),
                           'all_gather_bytes_per_step': int(gather), 'peer_store_fraction': m.peer_store_fraction() if m.fused else None,
-                          'rank0_layer_ms_spmm_barrier': layer_ms, 'l2': 'inputs larger than L2'},
+                          'rank0_layer_ms_spmm_barrier': layer_ms, 'check': err, 'l2': 'inputs larger than L2'},
                'gpu_launches': (len(m.layers) + 2) * K, 'clocks': clocks,
                'roofline': {'bound': 'hbm', 'kernel': 'whole network (CSR-equivalent algorithmic bytes: 8 B/nnz + activations)', 'achieved': hbm, 'peak': peak * world, 'unit': 'GB/s',
                             'frac': hbm / (peak * world), 'traffic': None, 'peak_source': peak_src + ' x n_gpus'}}
