@@ -172,6 +172,13 @@ def g_keygen():
         'fc_perm': dict(shape=(120, 1, 1), global_geometric='permutation', local_geometric='identity', global_photometric='identity', local_photometric='identity'),
         'bias': dict(shape=(2, 4, 4), global_geometric='identity', local_geometric='identity', global_photometric='uniform_random_bias', local_photometric='identity', gamma=1.0),
         'affine': dict(shape=(2, 4, 4), global_geometric='permutation', local_geometric='identity', global_photometric='uniform_random_affine', local_photometric='identity', beta=1.0, gamma=1.0),
+        # general (several entries per row) keys
+        'givens_local': dict(shape=(2, 8, 8), global_geometric='identity', local_geometric='givens_orthogonal', global_photometric='identity', local_photometric='identity', alpha=5.0, blocksize=4),
+        'givens_global': dict(shape=(3, 8, 8), global_geometric='givens_orthogonal', local_geometric='identity', global_photometric='identity', local_photometric='identity', alpha=30),
+        'doubly_stochastic': dict(shape=(2, 8, 8), global_geometric='identity', local_geometric='doubly_stochastic', global_photometric='identity', local_photometric='identity', alpha=3.0, blocksize=4),
+        'orthogonal_tiled': dict(shape=(2, 16, 16), global_geometric='hierarchical_permutation', hierarchical_blockshape=(2, 2), hierarchical_permute_at_level=(0, 1), global_photometric='identity',
+                                 local_geometric='givens_orthogonal', alpha=4, blocksize=4, local_photometric='uniform_random_affine', beta=0.1, gamma=100.0, memoryorder='block', tileshape=(4, 4)),
+        'givens_fc': dict(shape=(12, 1, 1), global_geometric='identity', local_geometric='givens_orthogonal', global_photometric='identity', local_photometric='uniform_random_gain', alpha=3.0, beta=1.0, blocksize=4),
     }
     names = []
     for (name, kw) in cases.items():

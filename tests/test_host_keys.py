@@ -50,6 +50,35 @@ def test_keygen_bias_keys_match_reference(name):
     assert np.allclose(I, np.eye(I.shape[0]), atol=1e-5)
 
 
+@pytest.mark.parametrize('name', ['givens_local', 'givens_global', 'doubly_stochastic', 'orthogonal_tiled', 'givens_fc'])
+def test_keygen_general_keys_match_reference(name):
+    """Givens-orthogonal / doubly-stochastic key families (several entries per row): same RNG draws, same structure, values
+    equal to the reference's (bit-equal for the Givens families; the doubly stochastic block passes through a dense
+    float64 inverse, compared to 1e-6)."""
+    import scipy.sparse
+    from keynet_b200.sparse import SparseKey
+    z = gu.load('keygen_kat.npz')
+    kw = gu.jstr(z, name + '.args')
+    shape = tuple(kw.pop('shape'))
+    for k in ('hierarchical_blockshape', 'hierarchical_permute_at_level', 'tileshape'):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    np.random.seed(11)
+    (A, Ainv) = system.keygen(shape, **kw)
+    tail = np.random.rand()
+    np.random.seed(11)
+    assert isinstance(A, SparseKey)
+    for (K, pre) in ((A, name + '.A'), (Ainv, name + '.Ainv')):
+        (shp, row, col, data) = gu.coo_arrays(z, pre)
+        ref = np.asarray(scipy.sparse.coo_matrix((data.astype(np.float64), (row, col)), shape=shp).todense())
+        got = K.todense().astype(np.float64)
+        assert np.array_equal(got != 0, ref != 0), pre
+        if name == 'doubly_stochastic':
+            assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), pre
+        else:
+            assert np.array_equal(got.astype(np.float32), ref.astype(np.float32)), pre
+
+
 def test_keygen_general_geometric_keys_are_inverse_pairs():
     """Givens-orthogonal / doubly stochastic options give general sparse keys (sparse.SparseKey) with A . Ainv = I."""
     from keynet_b200.sparse import SparseKey
