@@ -5,10 +5,11 @@ Workload (BASELINE.json configs[1]): CIFAR-10 AllConvNet 3x32x32, hierarchical b
 (`np.random.seed(0); Keynet((3,32,32), net, global_geometric='hierarchical_permutation',
 hierarchical_blockshape=(2,2), hierarchical_permute_at_level=(0,1))`), batch 4096 per GPU, synthetic
 images, numpy-seeded random-init weights.  One step = sensor.encrypt() + knet.forward() over one batch:
-1 layout kernel + 12 SpMM launches (+ReLU fused) + 1 layout kernel.
+1 encrypt kernel (homogenise + transpose + image key) + one or two SpMM launches per keyed layer (+ReLU fused) + 1 layout kernel.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--net acn|lenet]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--net acn|lenet|vgg16]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1: data-parallel replicas)
+  ... bench.py --gpus N --net vgg16 --batch 256 --parallel rows|rows-fused         (every keyed layer row-sharded: strong scaling)
   python bench.py --impl reference ...      (CPU arm: the oracle port of the reference's scipy path, all host threads)
 
 Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
@@ -426,7 +427,8 @@ def main():
         domW = [W for (name, W, _) in plan.layers if name == dom][0]
         grouped = domW._pg is not None and N >= 32 and N % 4 == 0
         on_tc = grouped and any(c['tc'] is not None for c in domW._pg.classes) and N >= 128
-        kname = ('pg_tc_kernel (tcgen05 3xTF32)' if on_tc else 'pg_simt_kernel / pg_small_kernel (fp32 FMA)') if grouped else 'spmm_rowwarp_kernel'
+        clustered = grouped and any(c.get('cg') is not None for c in domW._pg.classes)
+        kname = ('pg_tc_kernel (tcgen05 3xTF32)' if on_tc else ('pg_cluster_kernel (fp32 FMA, staged gathers)' if clustered else 'pg_simt_kernel / pg_small_kernel (fp32 FMA)')) if grouped else 'spmm_rowwarp_kernel'
         if grouped:
             kname += ', pattern groups (G, K_pad, n_groups)=%s' % str(domW._pg.summary()['classes'])
         hbm_achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
