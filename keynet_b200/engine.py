@@ -97,6 +97,43 @@ class ForwardPlan(object):
             raise ValueError('invalid affine vector: %d outputs lost the homogeneous coordinate' % int(bad.item()))
         return out
 
+    def run_host_many(self, batches, outs):
+        """End-to-end over a sequence of HOST batches (pinned), software-pipelined: the H2D copy of batch k+1 runs on a copy
+        stream while the chain of batch k runs on the compute stream (two device staging buffers); every batch still pays
+        its own H2D of the images and D2H of the logits.  outs: pinned host tensors [N, K], one per batch (may repeat).
+        Synchronises once at the end and checks the homogeneous coordinate of every batch."""
+        assert len(batches) == len(outs)
+        if not hasattr(self, '_stage'):
+            self._stage = [torch.empty_like(self.images) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+            self._h2d_done = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
+        self.bad.zero_()
+        for b in range(2):
+            self._stage_free[b].record(main)
+        def h2d(k):
+            b = k % 2
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._stage_free[b])          # the chain has consumed what was staged here
+                self._stage[b].copy_(batches[k].reshape(self.N, self.D), non_blocking=True)
+                self._h2d_done[b].record(self._copy_stream)
+        if len(batches) > 0:
+            h2d(0)
+        for k in range(len(batches)):
+            b = k % 2
+            if k + 1 < len(batches):
+                h2d(k + 1)
+            main.wait_event(self._h2d_done[b])
+            self.images.copy_(self._stage[b], non_blocking=True)           # device-to-device, then the staging buffer is free again
+            self._stage_free[b].record(main)
+            self._launch()
+            outs[k].copy_(self.logits, non_blocking=True)
+        bad = self.bad.cpu()               # synchronises the stream
+        if int(bad.item()) != 0:
+            raise ValueError('invalid affine vector: %d outputs lost the homogeneous coordinate' % int(bad.item()))
+        return outs
+
     def layer_times_ms_mean(self, n_sets):
         """Mean launch duration of every layer's SpMM over the first n_sets recorded steps."""
         assert self.layer_events is not None
