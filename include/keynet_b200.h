@@ -115,14 +115,14 @@ int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, 
  * Y[rows[i]][:] = relu?(sum_s part[s*G + i][:]) (and performs the peer stores of the row-sharded path). */
 int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
 
-/* Clustered variant for small groups (G <= 16; csrc/pgcluster.cu): the groups of a tile of neighbouring output pixels
+/* Clustered variant for short reductions (csrc/pgcluster.cu; G <= 256, walked 16 rows at a time above 16): the groups of a tile of neighbouring output pixels
  * form a cluster with ONE union column list that is staged in shared memory once per (cluster, 128 batch columns), so a
  * 3x3 convolution reads every X row from L2 about once instead of 9 times.
  *   cl_gptr[n_clusters+1]   group range of every cluster (groups are stored cluster by cluster)
  *   cl_uptr[n_clusters+1]   range of every cluster in ucols; at most KN_CG_MAX_UNION columns per cluster
  *   ucols                   union column lists
  *   lidx[n_groups][K_pad]   BYTE offset (local column index x 512) of every column of the group in the staged tile
- *   valsT[n_blocks][K_pad][GM]  value blocks k-major, GM = G rounded up to even (zero padded)
+ *   valsT[n_blocks][K_pad][GM]  value blocks k-major, GM = G rounded up to even (G <= 16) or to a multiple of 16 (zero padded)
  * rows / group_k / block_of as in kn_spmm_pg_f32.  u_max / g_max = largest union / group count of a cluster: the CTA stages
  * u_max x 512 B of X plus g_max x K_pad x 4 B of lidx, together at most KN_CG_MAX_UNION x 512 B. */
 #define KN_CG_MAX_UNION 224

@@ -32,7 +32,7 @@ template <int GM, bool RELU>
 __global__ void __launch_bounds__(kThreads, (GM > 8) ? 2 : 3)
 pg_cluster_kernel(const int32_t *__restrict__ cl_gptr, const int32_t *__restrict__ cl_uptr, const int32_t *__restrict__ ucols,
                   const int32_t *__restrict__ rows, const int32_t *__restrict__ lidx, const float *__restrict__ valsT,
-                  const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_clusters, int G, int K_pad, int u_max,
+                  const int32_t *__restrict__ group_k, const int32_t *__restrict__ block_of, int64_t n_clusters, int G, int K_pad, int u_max, int n_chunks, int gm_total,
                   const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -68,11 +68,16 @@ pg_cluster_kernel(const int32_t *__restrict__ cl_gptr, const int32_t *__restrict
 
     const unsigned char *__restrict__ sx = smem_raw + lane * 16;
     const int32_t *__restrict__ s_lidx = reinterpret_cast<const int32_t *>(smem_raw + (size_t)u_max * (TN * 4));
-    for (int g = g_beg + warp; g < g_end; g += kWarps) {
+    // work item = (group, chunk of GM rows): tall groups (first conv layer of an RGB network: G = 64 / 96 output channels over
+    // 28 taps) are walked GM rows at a time against the same staged rows
+    const int n_items = (g_end - g_beg) * n_chunks;
+    for (int item = warp; item < n_items; item += kWarps) {
+        const int g = g_beg + item / n_chunks;
+        const int r0 = (item - (g - g_beg) * n_chunks) * GM;
         const int K = group_k ? __ldg(group_k + g) : K_pad;
         const int64_t blk = block_of ? (int64_t)__ldg(block_of + g) : g;
         const int32_t *__restrict__ li = s_lidx + (g - g_beg) * K_pad;
-        const float *__restrict__ vt = valsT + blk * (int64_t)K_pad * GM;
+        const float *__restrict__ vt = valsT + blk * (int64_t)K_pad * gm_total + r0;
         float acc[GM][4];
 #pragma unroll
         for (int r = 0; r < GM; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f; }
@@ -81,7 +86,7 @@ pg_cluster_kernel(const int32_t *__restrict__ cl_gptr, const int32_t *__restrict
             const float4 x = *reinterpret_cast<const float4 *>(sx + li[k]);
 #pragma unroll
             for (int r2 = 0; r2 < GM; r2 += 2) {                                                   // GM even: exact row count for G = 6
-                const float2 a = __ldg(reinterpret_cast<const float2 *>(vt + k * GM + r2));       // warp-uniform: one L1 sector
+                const float2 a = __ldg(reinterpret_cast<const float2 *>(vt + k * gm_total + r2)); // warp-uniform: one L1 sector
                 acc[r2 + 0][0] = fmaf(a.x, x.x, acc[r2 + 0][0]); acc[r2 + 0][1] = fmaf(a.x, x.y, acc[r2 + 0][1]); acc[r2 + 0][2] = fmaf(a.x, x.z, acc[r2 + 0][2]); acc[r2 + 0][3] = fmaf(a.x, x.w, acc[r2 + 0][3]);
                 acc[r2 + 1][0] = fmaf(a.y, x.x, acc[r2 + 1][0]); acc[r2 + 1][1] = fmaf(a.y, x.y, acc[r2 + 1][1]); acc[r2 + 1][2] = fmaf(a.y, x.z, acc[r2 + 1][2]); acc[r2 + 1][3] = fmaf(a.y, x.w, acc[r2 + 1][3]);
             }
@@ -92,7 +97,7 @@ pg_cluster_kernel(const int32_t *__restrict__ cl_gptr, const int32_t *__restrict
                 int32_t yrows[2];
                 unsigned pmask[2];
 #pragma unroll
-                for (int i = 0; i < 2; i++) yrows[i] = (r4 + i < G) ? __ldg(rows + (int64_t)g * G + r4 + i) : 0;
+                for (int i = 0; i < 2; i++) yrows[i] = (r0 + r4 + i < G) ? __ldg(rows + (int64_t)g * G + r0 + r4 + i) : 0;
                 if (peers.n != 0) {
 #pragma unroll
                     for (int i = 0; i < 2; i++) pmask[i] = kn_peer_mask(peers, yrows[i]);
@@ -100,7 +105,7 @@ pg_cluster_kernel(const int32_t *__restrict__ cl_gptr, const int32_t *__restrict
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const int r = r4 + i;
-                    if (r < G) {
+                    if (r0 + r < G) {
                         float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                         if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
                         const int64_t yoff = (int64_t)yrows[i] * ldy + n0;
@@ -118,6 +123,7 @@ int launch_cluster(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
                    const int32_t *group_k, const int32_t *block_of, int64_t n_clusters, int G, int K_pad, int u_max, int g_max,
                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, bool relu, cudaStream_t s)
 {
+    const int n_chunks = (G + GM - 1) / GM, gm_total = n_chunks * GM;           // G <= 16: one chunk of GM = G rounded to even
     const int64_t n_tiles = kn_cdiv(n_vecs, TN), gx = n_clusters * n_tiles;
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm_cg: grid too large");
     const size_t smem = (size_t)u_max * TN * sizeof(float) + (size_t)g_max * K_pad * sizeof(int32_t);
@@ -128,8 +134,8 @@ int launch_cluster(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
         KN_CUDA(cudaFuncSetAttribute(pg_cluster_kernel<GM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KN_CG_MAX_UNION * TN * (int)sizeof(float)));
         configured = true;
     }
-    if (relu) pg_cluster_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, X, ldx, Y, ldy, n_vecs, kn_current_peers());
-    else      pg_cluster_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, X, ldx, Y, ldy, n_vecs, kn_current_peers());
+    if (relu) pg_cluster_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, n_chunks, gm_total, X, ldx, Y, ldy, n_vecs, kn_current_peers());
+    else      pg_cluster_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, n_chunks, gm_total, X, ldx, Y, ldy, n_vecs, kn_current_peers());
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -138,7 +144,7 @@ int launch_cluster(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
 KN_API int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t *ucols, const int32_t *rows, const int32_t *lidx, const float *valsT,
                           const int32_t *group_k, const int32_t *block_of, int64_t n_clusters, int32_t G, int32_t K_pad, int32_t u_max, int32_t g_max,
                           const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
-    KN_REQUIRE(n_clusters >= 0 && G > 0 && G <= 16 && K_pad > 0, "spmm_cg: bad shape (G=%d K_pad=%d)", G, K_pad);
+    KN_REQUIRE(n_clusters >= 0 && G > 0 && G <= 256 && K_pad > 0, "spmm_cg: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(g_max > 0 && K_pad % 32 == 0, "spmm_cg: bad g_max / K_pad");
     KN_REQUIRE(u_max > 0 && u_max <= KN_CG_MAX_UNION, "spmm_cg: union of %d columns does not fit the staging tile (max %d)", u_max, KN_CG_MAX_UNION);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_cg: bad leading dimension");
@@ -149,6 +155,7 @@ KN_API int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const 
     cudaStream_t s = (cudaStream_t)stream;
     const bool relu = (flags & KN_SPMM_RELU) != 0;
 #define KN_CG(GM) return launch_cluster<GM>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, g_max, X, ldx, Y, ldy, n_vecs, relu, s)
+    if (G > 16) KN_CG(16);            // chunks of 16 rows: valsT[block][K_pad][G rounded up to 16]
     switch ((G + 1) / 2) {            // GM = G rounded up to even: valsT[block][K_pad][GM]
         case 1: KN_CG(2);
         case 2: KN_CG(4);

@@ -972,7 +972,7 @@ class PatternGroups(object):
                     cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
                 if cls['tc'] is not None and ng == 1 and Kl[b0] >= PatternGroups.SPLITK_MIN_K:
                     cls['splitk'] = PatternGroups._split_k(cls, int(Kl[b0]))
-                if cid is not None and int(G) <= PatternGroups.CG_KERNEL_MAX_G and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
+                if cid is not None and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
                     cls['cg'] = PatternGroups._cluster(cls, cid, C)
                 pg.classes.append(cls)
                 in_group[rows64] = True
@@ -1018,9 +1018,10 @@ class PatternGroups(object):
         return dict(S=S, G=G, K_pad=Kp, rows=torch.arange(S * G, dtype=torch.int32, device=dev), cols=cols_s.reshape(-1), group_k=group_k,
                     tc=dict(hi=vhi, lo=vlo, maps=maps), part={})
 
-    CG_MAX_G = 16            # groups up to this height are ordered by their spatial hint (L1 / L2 locality of the gathers)
-    CG_KERNEL_MAX_G = 8      # ... and run on the clustered kernel when the reduction is short: there the product is bound by
-    CG_KERNEL_MAX_K = 32     # L2 -> SM gather traffic (measured: LeNet conv1 0.48 -> 0.38 ms; conv2 G=16 K=55 is FMA-bound: pg_small)
+    CG_MAX_G = 128           # groups up to this height are ordered by their spatial hint (L1 / L2 locality of the gathers)
+    CG_KERNEL_MAX_K = 32     # ... and run on the clustered kernel when the reduction is short (K_pad <= 32: first conv layers,
+                             # 1 or 3 input channels): there the product is bound by L2 -> SM gather traffic and per-CTA latency
+                             # (measured: LeNet conv1 0.48 -> 0.34 ms); LeNet conv2 (G=16, K=55) is FMA-bound: pg_small
     CG_MAX_UNION = 224       # KN_CG_MAX_UNION: rows of the staged tile (224 x 512 B = 112 KB, two CTAs per SM)
     CG_MAX_BYTES = 256 << 20
 
@@ -1030,7 +1031,7 @@ class PatternGroups(object):
         offsets into the staged tile, k-major value blocks.  cid: sorted int64 cluster id of every group."""
         (G, K_pad, ng) = (cls['G'], cls['K_pad'], cls['n_groups'])
         dev = cid.device
-        GM = (G + 1) // 2 * 2
+        GM = (G + 1) // 2 * 2 if G <= 16 else (G + 15) // 16 * 16
         n_blocks = cls['n_blocks']
         if (n_blocks * K_pad * GM + ng * K_pad) * 4 > PatternGroups.CG_MAX_BYTES:
             return None
@@ -1253,7 +1254,9 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_gr
         # pattern groups come from the STRUCTURAL matrix (exact zeros kept): every output pixel keeps its full
         # M-row group even where the reference's offset rounding turned a tiny weight into a dropped zero
         S = SparseMatrix(((n, Kp), *_keycompile(csr0, n, K, A, Ainv, dev, row_scale_slice=sel, keep_zeros=True)), device=dev)
-        hint = _pixel_tile_hint(ids, n, (M, U // stride, V // stride), C, P, stride, False, dev) if M <= PatternGroups.CG_MAX_G else None
+        # spatial clusters only where the clustered kernel applies: short reductions (first conv layer: 1 or 3 input channels)
+        clustered = M <= PatternGroups.CG_MAX_G and (C * P * Q + 1 + 31) // 32 * 32 <= PatternGroups.CG_KERNEL_MAX_K
+        hint = _pixel_tile_hint(ids, n, (M, U // stride, V // stride), C, P, stride, False, dev) if clustered else None
         W._pg = PatternGroups.build(S, hint=hint)
     return W
 
