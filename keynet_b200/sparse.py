@@ -1261,7 +1261,7 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_gr
     return W
 
 
-def _pixel_tile_hint(ids, n, outshape, C, k, stride, depthwise, dev, tile=None):
+def _pixel_tile_hint(ids, n, outshape, C, k, stride, depthwise, dev):
     """Spatial cluster id of every compiled row: rows whose underlying Toeplitz row lies in the same t x t tile of output
     pixels (and, for pooling, the same channel) share an id.  t is the largest tile whose union of taps fits the staging
     buffer of the clustered kernel; None if not even one pixel does.  ids: Toeplitz row of every compiled row (None = identity)."""
@@ -1269,19 +1269,17 @@ def _pixel_tile_hint(ids, n, outshape, C, k, stride, depthwise, dev, tile=None):
     K_pad = ((k * k * (1 if depthwise else C) + 1) + 31) // 32 * 32
     # staged bytes of a t x t tile: union rows x 512 B + one lidx row (K_pad ints) per group
     staged = lambda t: (((t - 1) * stride + k) ** 2 * (1 if depthwise else C) + 1) * 512 + t * t * K_pad * 4
-    if tile is None:
-        t = 0
-        while t < max(Uo, Vo) and staged(t + 1) <= PatternGroups.CG_MAX_UNION * 512:
-            t += 1
-        if t == 0:
-            return None
-        t = min(t, max(Uo, Vo))
-        for d in range(t, max(1, t // 2), -1):          # prefer a tile that divides the image (equal clusters)
-            if Uo % d == 0 and Vo % d == 0:
-                t = d
-                break
-        tile = (t, t)
-    (th, tw) = tile
+    t = 0
+    while t < max(Uo, Vo) and staged(t + 1) <= PatternGroups.CG_MAX_UNION * 512:
+        t += 1
+    if t == 0:
+        return None
+    t = min(t, max(Uo, Vo))
+    for d in range(t, max(1, t // 2), -1):          # prefer a tile that divides the image (equal clusters)
+        if Uo % d == 0 and Vo % d == 0:
+            t = d
+            break
+    (th, tw) = (t, t)
     src = ids if ids is not None else torch.arange(n, dtype=torch.int64, device=dev)
     px = src % (Uo * Vo)
     ch = src // (Uo * Vo)
@@ -1314,22 +1312,6 @@ def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, c
     csr = _toeplitz_rows(desc, wq, None, ids, n, dev)
     csr = _keycompile(csr, n, K, A, Ainv, dev, row_scale_slice=sel)
     W = SparseMatrix(((n, Kp), *csr), device=dev)
-    if W.nnz() >= 4096 and os.environ.get('KN_POOL_ORDER', '1') == '1':
-        # every pooling row has its own column set (one channel): no pattern groups.  Rows of neighbouring pixels of a
-        # channel still share taps, so the CSR kernel walks them in (channel, pixel tile) order -- the 8 rows of a CTA then
-        # hit each other's X rows in L1 whatever permutation the keys apply.
-        hint = _pixel_tile_hint(ids, n, (C, U // stride, V // stride), C, k, stride, True, dev, tile=(2, 4))
-        order = torch.argsort(hint, stable=True)
-        (indptr, indices, data) = csr
-        csr2 = _two_phase(
-            n,
-            lambda row_nnz: check(_native.lib().kn_csr_gather_rows_count(ptr(indptr), ptr(order), n, ptr(row_nnz), stream_ptr())),
-            lambda ip, ix, dt: check(_native.lib().kn_csr_gather_rows_fill(ptr(indptr), ptr(indices), ptr(data), ptr(order), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
-            dev)
-        pg = PatternGroups()
-        pg.shape = W.shape
-        pg.rest = dict(n=n, indptr=csr2[0], indices=csr2[1], data=csr2[2], out_rows=order.to(torch.int32))
-        W._pg = pg
     return W
 
 

@@ -174,3 +174,26 @@ def test_spy_renders_keys_and_blocks():
     assert im.mode == 'RGB' and max(im.size) == 128
     im2 = sparse.spy(sparse.SparseKey.from_monomial(P), mindim=512, showdim=256, range=(0, 100), eps=0.5)
     assert max(im2.size) == 256
+
+
+def test_pixel_tile_hint_clusters_rows_by_output_tile():
+    """Spatial cluster ids of the clustered kernel (sparse._pixel_tile_hint): rows whose Toeplitz row lies in the same tile of
+    output pixels share an id whatever the output key; the homogeneous row gets an id of its own."""
+    import torch
+    from keynet_b200.sparse import _pixel_tile_hint
+    (M, Uo, Vo, C, k) = (6, 28, 28, 1, 3)
+    rs = np.random.RandomState(0)
+    perm = np.concatenate([rs.permutation(M * Uo * Vo), [M * Uo * Vo]])           # output key: row r of W_hat = Toeplitz row perm[r]
+    hint = _pixel_tile_hint(torch.from_numpy(perm), len(perm), (M, Uo, Vo), C, k, 1, False, 'cpu').numpy()
+    px = perm[:-1] % (Uo * Vo)
+    (py, pxx) = (px // Vo, px % Vo)
+    t = 7                                                                            # largest tile whose union fits, dividing 28
+    assert np.array_equal(hint[:-1], (py // t) * (Vo // t) + pxx // t)
+    assert hint[-1] == (Uo // t) * (Vo // t) and hint[-1] not in hint[:-1]
+    # all channels of a pixel land in the same cluster; a cluster holds t*t pixels x M channels
+    assert np.all(np.bincount(hint[:-1]) == t * t * M)
+    # depthwise (pooling): clusters are per channel
+    hp = _pixel_tile_hint(None, M * 14 * 14 + 1, (M, 14, 14), M, 3, 2, True, 'cpu').numpy()
+    assert len(np.unique(hp[:-1])) % M == 0 and hp[-1] not in hp[:-1]
+    # a reduction too long for the staging buffer: no clustering
+    assert _pixel_tile_hint(None, 10, (4, 3, 3), 512, 3, 1, False, 'cpu') is None
