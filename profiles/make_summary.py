@@ -27,7 +27,7 @@ for r in rows[hi + 1:]:
     t = float(r[vi].replace(',', ''))
     per_launch.append((name, r[gi], t))
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += t
-FORWARD = ('pg_tc_kernel', 'pg_simt_kernel', 'pg_small_kernel', 'pg_cluster_kernel', 'spmm_', 'affine_to_linear_t', 'linear_to_affine_t')
+FORWARD = ('pg_tc_kernel', 'pg_simt_kernel', 'pg_small_kernel', 'pg_cluster_kernel', 'spmm_', 'affine_to_linear_t', 'linear_to_affine_t', 'encrypt_monomial_t', 'splitk_reduce')
 fwd = collections.OrderedDict((k, v) for (k, v) in agg.items() if k.startswith(FORWARD))
 build = collections.OrderedDict((k, v) for (k, v) in agg.items() if not k.startswith(FORWARD))
 tot = sum(v[1] for v in fwd.values())
