@@ -11,10 +11,13 @@ digests) -- no reference source is copied.
 Goldens (all little-endian .npz / .json):
   toeplitz_kat.npz        reference sparse_toeplitz_conv2d / avgpool2d on the shapes of
                           test/test_sparse.py:223,251 (+ a multi-channel case)
-  keygen_kat.npz          reference keygen() outputs (A, Ainv) for several option sets
+  keygen_kat.npz          reference keygen() outputs (A, Ainv) for several option sets, incl. the general key families
+                          (Givens-orthogonal, doubly stochastic, the TiledOrthogonalKeynet option set)
   blockpermute_kat.npz    reference hierarchical_block_permutation_matrix()
   lenet_cfg1.npz          np.random.seed(0); PermutationKeynet(LeNet_AvgPool) (SURVEY §8d cfg 1)
   lenet_cfg3.npz          np.random.seed(0); Keynet(permutation + uniform_random_gain) (cfg 3)
+  lenet_givens.npz        the reference's LeNet orthogonal configuration (test/test_keynet.py:180-197): Givens local keys +
+                          affine photometric keys + hierarchical rotation, block memory order -- general-key compile
   challenge_kat.npz       demo/keynet_challenge_lenet_10AUG20.{pkl,png} known-answer test
   acn_cfg2.json           AllConvNet hierarchical-permutation keynet: per-layer nnz + sha256
   vggtwin_cfg5.json       reduced-channel twins of VGG16 layers, permutation keys: nnz + sha256
