@@ -29,8 +29,17 @@ def plan_rows(module, outshape, world, A=None):
     what lets the fused path (peer row masks) replace the all-gather by a halo exchange."""
     (C, H, W) = [int(s) for s in outshape]
     R = C * H * W
-    src = np.arange(R, dtype=np.int64) if A is None else np.asarray(A.perm[:R], dtype=np.int64)   # Toeplitz row of every W_hat row
-    assert A is None or (len(A.perm) == R + 1 and src.max() < R), 'output key must be homogeneous'
+    if A is None:
+        src = np.arange(R, dtype=np.int64)
+    elif hasattr(A, 'perm'):
+        src = np.asarray(A.perm[:R], dtype=np.int64)            # Toeplitz row of every W_hat row
+        assert len(A.perm) == R + 1, 'output key must be homogeneous'
+    else:
+        # general key (several entries per row): the first stored column stands in for the row's position -- block-local
+        # keys mix rows of one small spatial block, so this keeps the cut spatial; any assignment of rows to ranks is valid
+        assert A.shape[0] == R + 1, 'output key must be homogeneous'
+        src = np.minimum(np.asarray(A.indices[A.indptr[:-1][:R]], dtype=np.int64), R - 1)
+    assert src.max() < R, 'output key must be homogeneous'
     if isinstance(module, (nn.Conv2d, nn.AvgPool2d)) and H * W > 1:
         (channel, pixel) = (src // (H * W), src % (H * W))
         order = np.argsort(pixel * C + channel, kind='stable').astype(np.int64)       # (pixel, channel) <- (channel, pixel)

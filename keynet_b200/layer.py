@@ -41,8 +41,11 @@ class KeyedLayer(nn.Module):
         if isinstance(A, SparseKey) or isinstance(Ainv, SparseKey):
             # general keys (Givens-orthogonal / doubly stochastic blocks, keynet/system.py:398-410): the un-keyed layer matrix,
             # then the two products of keynet/layer.py:35,46,59,70 as GPU SpGEMMs (csrc/spgemm.cu)
-            assert rows is None and col_remap is None, 'row-sharded compile supports monomial keys'
             self._init_general(module, inshape, outshape, A, Ainv)
+            if rows is not None or col_remap is not None:
+                # row shard of a general-key layer: the full W_hat is compiled (general keys are used on small networks), then
+                # this rank's rows are gathered and the columns moved to their gathered positions
+                self.W = sparse.shard_compiled(self.W, rows, col_remap, n_cols_phys)
             self._finish(module, inshape, outshape, tileshape, keep_csr, t0)
             return
 

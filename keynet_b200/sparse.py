@@ -1292,6 +1292,31 @@ def _pixel_tile_hint(ids, n, outshape, C, k, stride, depthwise, dev):
     return torch.where(src < M * Uo * Vo, hint, torch.full_like(hint, n_ids))        # homogeneous row: a cluster of its own
 
 
+def shard_compiled(W, rows, col_remap, n_cols_phys):
+    """Rows `rows` ((r0, r1) or an index array, in that order) of an already compiled W_hat, with column c moved to position
+    col_remap[c] of a buffer with n_cols_phys rows (dist.py).  Used for general-key layers; monomial keys shard at build time."""
+    dev = W._data.device
+    L = _native.lib()
+    (R, K) = W.shape
+    if rows is None:
+        ids = torch.arange(R, dtype=torch.int64, device=dev)
+    elif isinstance(rows, tuple):
+        ids = torch.arange(int(rows[0]), int(rows[1]), dtype=torch.int64, device=dev)
+    else:
+        ids = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(dev)
+    n = int(ids.numel())
+    csr = _two_phase(
+        n,
+        lambda row_nnz: check(L.kn_csr_gather_rows_count(ptr(W._indptr), ptr(ids), n, ptr(row_nnz), stream_ptr())),
+        lambda ip, ix, dt: check(L.kn_csr_gather_rows_fill(ptr(W._indptr), ptr(W._indices), ptr(W._data), ptr(ids), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
+        dev)
+    Kp = K
+    if col_remap is not None:
+        (Kmap, Kp) = _remapped(MonomialKey(np.arange(K)), col_remap, n_cols_phys)
+        csr = _keycompile(csr, n, K, None, Kmap, dev)
+    return SparseMatrix(((n, Kp), *csr), device=dev)
+
+
 def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
     """W_hat = A . toeplitz(avgpool) . Ainv (keynet/layer.py:56-59).  The reference builds C*C channel
     pairs and lets the SpGEMM drop the zero ones; here only the channel diagonal is generated."""

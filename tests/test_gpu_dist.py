@@ -78,3 +78,19 @@ def test_sharded_model_world2(fused, selective):
         if fused and selective:
             assert frac is not None and frac < 0.95, frac          # fewer stores than a full all-gather
     assert abs(res[0][3] - res[1][3]) < 0.2 * max(res[0][3], res[1][3])      # shards are balanced
+
+
+def test_sharded_model_world1_general_keys():
+    """Row-sharded compile of general-key layers (Givens + affine keys): full compile, then row gather + column remap."""
+    from keynet_b200 import dist as kdist, system
+    kw = dict(local_geometric='givens_orthogonal', alpha=2.0, blocksize=7, local_photometric='uniform_random_affine', beta=1.0, gamma=1.0)
+    x = torch.randn(64, 1, 28, 28, generator=torch.Generator().manual_seed(1))
+    np.random.seed(0)
+    (sensor, knet) = system.Keynet((1, 28, 28), _net(), **kw)
+    xc = sensor.fromtensor(x).encrypt().astensor()
+    y_ref = knet.forward(xc).reshape(64, -1).numpy()
+    np.random.seed(0)
+    m = kdist.ShardedKeyedModel((1, 28, 28), _net(), rank=0, world=1, **kw)
+    y = m.forward(xc).reshape(64, -1).cpu().numpy()
+    assert np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)
+    assert np.allclose(y, _net()(x).detach().numpy(), atol=2e-4)
