@@ -190,6 +190,15 @@ def oracle_layers_on_cpu(wl):
     return [(ko.monomial_key(A.perm, A.scale), False)] + [(r.W, r.relu) for r in recorded]
 
 
+def host_threads():
+    """Host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone
+    and is meant to use all the host threads it can, so the OpenMP default is not what we want there.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_oracle(layers, inshape, n_images, threads, repeats=1):
     from oracle import keynet_oracle as ko
     rs = np.random.RandomState(0)
@@ -205,8 +214,7 @@ def time_oracle(layers, inshape, n_images, threads, repeats=1):
 
 
 def cpu_baseline(layers, inshape, budget_s=15.0):
-    from oracle import keynet_oracle as ko
-    threads = ko.max_threads()
+    threads = host_threads()
     t_probe = time_oracle(layers, inshape, 32, threads)
     n = int(max(32, min(16384, (budget_s / max(t_probe / 32.0, 1e-6)))))
     dt = time_oracle(layers, inshape, n, threads)
@@ -221,7 +229,7 @@ def run_reference(args, rank, world):
     from oracle import keynet_oracle as ko
     wl = workload(args.net)
     layers = oracle_layers_on_cpu(wl)
-    threads = ko.max_threads()
+    threads = host_threads()
     t_probe = time_oracle(layers, wl['inshape'], 2, threads)
     n = int(max(1, min(64, 4.0 / max(t_probe / 2.0, 1e-6))))       # ~4 s of CPU work per step
     for _ in range(max(1, min(args.warmup, 1))):
