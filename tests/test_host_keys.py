@@ -197,3 +197,19 @@ def test_pixel_tile_hint_clusters_rows_by_output_tile():
     assert len(np.unique(hp[:-1])) % M == 0 and hp[-1] not in hp[:-1]
     # a reduction too long for the staging buffer: no clustering
     assert _pixel_tile_hint(None, 10, (4, 3, 3), 512, 3, 1, False, 'cpu') is None
+
+
+def test_key_serialisation_roundtrip_all_key_kinds():
+    """io._key_state / _key_load: monomial, monomial + bias column and general sparse keys survive the flat-tensor form."""
+    from keynet_b200 import io as kio
+    from keynet_b200.sparse import SparseKey, MonomialKey
+    np.random.seed(2)
+    (A, _) = system.keygen((2, 4, 4), 'permutation', 'identity', 'uniform_random_gain', 'identity', beta=1.0)
+    (B, _) = system.keygen((2, 4, 4), 'permutation', 'identity', 'uniform_random_affine', 'identity', beta=1.0, gamma=1.0)
+    (C, _) = system.keygen((2, 4, 4), 'identity', 'givens_orthogonal', 'identity', 'identity', alpha=3, blocksize=2)
+    for K in (A, B, C):
+        K2 = kio._key_load(kio._key_state(K))
+        assert type(K2) is type(K)
+        assert np.array_equal(K2.todense(), K.todense())
+    assert kio._key_load(kio._key_state(None)) is None
+    assert isinstance(C, SparseKey) and isinstance(B, MonomialKey) and B.has_bias()
