@@ -97,7 +97,7 @@ def profiled_traffic(net, batch, layer):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, gpu_index):
@@ -107,7 +107,7 @@ class ClockSampler(object):
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -122,6 +122,14 @@ class ClockSampler(object):
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        if len(self.rows) < 2:
+            # a very short timed region can end before the sampler's second reading: add one taken right now (GPU still loaded)
+            try:
+                r = subprocess.run(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=10)
+                self.rows.extend([l.strip() for l in r.stdout.splitlines() if l.strip()])
+            except Exception:
+                pass
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
