@@ -178,15 +178,21 @@ class ShardedKeyedModel(object):
         return self._symm[N]
 
     def _forward_fused(self, X, N, dev):
+        """Layer k writes ping-pong buffer (k + parity) % 2 on every rank that needs the row; one symmetric-memory barrier
+        per layer.  The parity flips by the layer count from one forward to the next, so the first layer of forward f+1
+        never stores into the buffer that still holds the output of forward f (a fast peer may run ahead by up to one
+        layer: its stores would otherwise race this rank's read of the logits)."""
         from . import _native
         from .sparse import spmm
+        assert N >= 32 and N % 4 == 0, 'fused row-sharded forward runs on batches padded to a multiple of 4, at least 32 (forward_linear pads)'
         bufs = self._symm_buffers(N, dev)
         masks = self._peer_masks(dev) if self.selective else [None] * len(self.layers)
+        parity = getattr(self, '_parity', 0)
         for (k, L) in enumerate(self.layers):
             sh = L._shard
             relu = L._fused_relu or ('ReLU' in L._layertype)
             self._stamp()
-            (t, h) = bufs[k % 2]
+            (t, h) = bufs[(k + parity) % 2]
             Yfull = t[:sh.n_phys * N].view(sh.n_phys, N)
             n_mine = len(sh.my_rows)
             slot = self.rank * sh.chunk * N * 4                         # byte offset of this rank's slot in every buffer
@@ -201,6 +207,7 @@ class ShardedKeyedModel(object):
             h.barrier()                                                 # every rank's stores have landed everywhere
             X = Yfull
         self._stamp()
+        self._parity = (parity + len(self.layers)) % 2
         return X
 
     def _stamp(self):
@@ -228,9 +235,13 @@ class ShardedKeyedModel(object):
         X = x_cipher.to(dev).t().contiguous()                         # feature-major [D+1, N]
         N = X.shape[1]
         if self.fused:
-            X = self._forward_fused(X, N, dev)
-            pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
-            return X[pos].t().contiguous()
+            Np = max(32, (N + 3) // 4 * 4)                              # granularity of the grouped kernels (peer stores use ld = Np)
+            if Np != N:
+                Xp = torch.zeros((X.shape[0], Np), dtype=torch.float32, device=dev)
+                Xp[:, :N] = X
+                X = Xp
+            X = self._forward_fused(X, Np, dev)
+            return X[self._out_positions(dev)][:, :N].t().contiguous()
         for L in self.layers:
             sh = L._shard
             relu = L._fused_relu or ('ReLU' in L._layertype)
@@ -249,8 +260,56 @@ class ShardedKeyedModel(object):
             X = Yfull
         self._stamp()
         # last layer: undo the shard-major order (a gather of K+1 rows)
-        pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
-        return X[pos].t().contiguous()
+        return X[self._out_positions(dev)].t().contiguous()
+
+    def _out_positions(self, dev):
+        if getattr(self, '_pos', None) is None:
+            self._pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
+        return self._pos
+
+    def forward_host_many(self, batches, outs):
+        """End to end over a sequence of pinned HOST batches [N, C, H, W] (the same batch on every rank): H2D, sensor
+        encryption, the sharded chain, D2H of the N x K logits into outs[k] (pinned).  The H2D copy of batch k+1 runs on a
+        copy stream while the chain of batch k runs.  Checks the homogeneous coordinate of every batch at the end."""
+        from . import _native
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if not hasattr(self, '_h2d'):
+            self._h2d = dict(stream=torch.cuda.Stream(), stage=[None, None], done=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)])
+        st = self._h2d
+        main = torch.cuda.current_stream()
+        for b in range(2):
+            st['free'][b].record(main)
+
+        def h2d(k):
+            b = k % 2
+            with torch.cuda.stream(st['stream']):
+                st['stream'].wait_event(st['free'][b])
+                if st['stage'][b] is None or st['stage'][b].shape != batches[k].shape:
+                    st['stage'][b] = torch.empty(batches[k].shape, dtype=torch.float32, device=dev)
+                st['stage'][b].copy_(batches[k], non_blocking=True)
+                st['done'][b].record(st['stream'])
+        if len(batches) > 0:
+            h2d(0)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        for k in range(len(batches)):
+            b = k % 2
+            if k + 1 < len(batches):
+                h2d(k + 1)
+            main.wait_event(st['done'][b])
+            x = st['stage'][b]
+            (N, D) = (int(x.shape[0]), int(np.prod(x.shape[1:])))
+            X = torch.empty((D + 1, N), dtype=torch.float32, device=dev)
+            self.sensor.encrypt_into(x.reshape(N, D), X)
+            st['free'][b].record(main)
+            y = self.forward_linear(X.t())                              # [N, K+1]; .t() of a transposed view is free
+            K = y.shape[1] - 1
+            logits = torch.empty((N, K), dtype=torch.float32, device=dev)
+            _native.check(_native.lib().kn_linear_to_affine_t(_native.ptr(y.t().contiguous()), N, N, K, _native.ptr(logits), 1e-3, _native.ptr(bad), _native.stream_ptr()))
+            outs[k].copy_(logits, non_blocking=True)
+        nbad = int(bad.cpu().item())
+        if nbad != 0:
+            raise ValueError('invalid affine vector: %d outputs lost the homogeneous coordinate' % nbad)
+        return outs
 
     def forward(self, x_cipher):
         from . import torch as ktorch

@@ -708,6 +708,7 @@ class SparseMatrix(object):
         (self._indptr, self._indices, self._data) = _keycompile((self._indptr, self._indices, self._data), self.shape[0], self.shape[1],
                                                                 None, A, self._data.device)
         self.shape = (self.shape[0], A.shape[1])
+        self._pg = None                    # the grouped execution form described the old matrix
         return self
 
     def _left_general(self, A):
@@ -744,6 +745,7 @@ class SparseMatrix(object):
         indptr[1:] = torch.cumsum(counts, 0)
         (self._indptr, self._indices, self._data) = (indptr, rows[order].to(torch.int32).contiguous(), self._data[order].contiguous())
         self.shape = (C, R)
+        self._pg = None
         return self
 
     def tocsr(self):
@@ -1113,6 +1115,9 @@ def spmm(W, x, relu=False, out=None):
     if W._data is None:
         # CSR was dropped (drop_csr): narrow / ragged batches are padded to the grouped kernels' granularity
         Np = max(32, (N + 3) // 4 * 4)
+        # the grouped kernels would store into the peers' buffers with leading dimension Np: the fused row-sharded path
+        # must pad its batch itself (dist.ShardedKeyedModel does)
+        assert not _native.current_output_peers()[0], 'ragged batch on a dropped-CSR matrix while output peers are set'
         xp = torch.zeros((x.shape[0], Np), dtype=torch.float32, device=x.device)
         xp[:, :N] = x
         yp = torch.empty((R, Np), dtype=torch.float32, device=x.device)
@@ -1200,8 +1205,9 @@ def _remapped(Ainv, col_remap, n_cols_phys):
         return (Ainv, Ainv.shape[0])
     col_remap = np.ascontiguousarray(col_remap, dtype=np.int64)
     assert len(col_remap) == Ainv.shape[0] and n_cols_phys > int(col_remap.max())
-    K = MonomialKey(Ainv.perm, Ainv.scale)
-    K.perm = col_remap[Ainv.perm]            # no longer square: only used as (col_map, col_scale) by _keycompile
+    K = MonomialKey(Ainv.perm, Ainv.scale, Ainv.bias)          # the bias column rides along: position[R] is the last physical row
+    assert Ainv.bias is None or int(col_remap[-1]) == int(n_cols_phys) - 1, 'homogeneous coordinate must stay the last gathered row'
+    K.perm = col_remap[Ainv.perm]            # no longer square: only used as (col_map, col_scale, col_bias) by _keycompile
     K.shape = (Ainv.shape[0], int(n_cols_phys))
     return (K, int(n_cols_phys))
 

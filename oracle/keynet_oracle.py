@@ -51,6 +51,10 @@ def lib():
         i64, i32p, i64p, f32p, f64p = ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
         L.ko_toeplitz_conv2d_coo.restype = ctypes.c_int64
         L.ko_toeplitz_conv2d_coo.argtypes = [ctypes.c_int] * 7 + [f32p, i32p, i32p, f32p]
+        L.ko_toeplitz_conv2d_coo_pixels.restype = ctypes.c_int64
+        L.ko_toeplitz_conv2d_coo_pixels.argtypes = [ctypes.c_int] * 7 + [f32p, i64, i64p, i32p, i32p, f32p]
+        L.ko_toeplitz_conv2d_emitted_min.restype = ctypes.c_float
+        L.ko_toeplitz_conv2d_emitted_min.argtypes = [ctypes.c_int] * 7 + [f32p]
         L.ko_coo_tocsr.restype = ctypes.c_int64
         L.ko_coo_tocsr.argtypes = [i64, i64, i32p, i32p, f32p, i64p, i32p, f32p]
         L.ko_csr_matmat_maxnnz.restype = ctypes.c_int64
@@ -169,6 +173,81 @@ def toeplitz_conv2d(inshape, f, bias=None, stride=1):
     cols = np.concatenate([cols, bcols, np.array([K], dtype=np.int32)])
     vals = np.concatenate([vals, bvals, np.array([1.0], dtype=np.float32)])
     return csr_from_coo((R + 1, K + 1), rows, cols, vals)
+
+
+def toeplitz_conv2d_pixels(inshape, f, bias, stride, pixels):
+    """ROW BAND of toeplitz_conv2d(inshape, f, bias, stride): only the rows of the output pixels `pixels` (ku*Vo + kv) are
+    populated -- all M channel rows of each -- plus the last row e_last; every other row is empty.  Same shape, same
+    global row / column numbers and the same offset rounding as the full matrix (the offset uses the minimum over the
+    FULL emission, keynet/sparse.py:184), so  band.rows == full.rows  on the populated rows (tests/test_oracle_bands.py).
+    For layers the host cannot hold (VGG16 conv1_2: 1.8 G entries)."""
+    (C, U, V) = [int(s) for s in inshape]
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    (M, C2, P, Q) = f.shape
+    assert C2 == C and P == Q and P % 2 == 1 and bias is not None
+    (Uo, Vo) = (U // stride, V // stride)
+    pixels = np.unique(np.asarray(pixels, dtype=np.int64))
+    assert len(pixels) == 0 or (pixels[0] >= 0 and pixels[-1] < Uo * Vo)
+    cap = len(pixels) * C * M * P * Q
+    rows = np.zeros(max(cap, 1), dtype=np.int32); cols = np.zeros(max(cap, 1), dtype=np.int32); vals = np.zeros(max(cap, 1), dtype=np.float32)
+    n = lib().ko_toeplitz_conv2d_coo_pixels(C, U, V, M, P, Q, int(stride), _p(f), len(pixels), _p(pixels), _p(rows), _p(cols), _p(vals))
+    (rows, cols, vals) = (rows[:n], cols[:n], vals[:n].copy())
+    mn = np.float32(lib().ko_toeplitz_conv2d_emitted_min(C, U, V, M, P, Q, int(stride), _p(f)))
+    offset = np.float32(np.abs(mn) + np.float32(1.0))
+    vals += offset
+    vals -= offset
+    (R, K) = (M * Uo * Vo, C * U * V)
+    bias = np.asarray(bias, dtype=np.float32)
+    boff = np.float32(np.abs(np.min(bias)) + np.float32(1.0))
+    brows = (np.arange(M, dtype=np.int64).reshape(-1, 1) * (Uo * Vo) + pixels.reshape(1, -1)).reshape(-1).astype(np.int32)
+    bvals = np.repeat(bias, len(pixels)).astype(np.float32)
+    bvals = (bvals + boff).astype(np.float32)
+    bvals -= boff
+    rows = np.concatenate([rows, brows, np.array([R], dtype=np.int32)])
+    cols = np.concatenate([cols, np.full(len(brows), K, dtype=np.int32), np.array([K], dtype=np.int32)])
+    vals = np.concatenate([vals, bvals, np.array([1.0], dtype=np.float32)])
+    return csr_from_coo((R + 1, K + 1), rows, cols, vals)
+
+
+def toeplitz_avgpool2d_pixels(inshape, kernel_size, stride, pixels):
+    """Row band of toeplitz_avgpool2d (dense-channel filter: C*C channel pairs per pixel, mostly explicit zeros)."""
+    C = int(inshape[0])
+    F = np.zeros((C, C, kernel_size, kernel_size), dtype=np.float32)
+    for k in range(C):
+        F[k, k, :, :] = 1.0 / (kernel_size * kernel_size)
+    return toeplitz_conv2d_pixels(inshape, F, np.zeros(C, dtype=np.float32), stride, pixels)
+
+
+def linear_matrix_rows(weight, bias, rows):
+    """Row band of linear_matrix: rows `rows` (< out) of [[W, b],[0, 1]] plus the last row, every other row empty."""
+    weight = np.asarray(weight, dtype=np.float32)
+    (out, inn) = weight.shape
+    rows = np.unique(np.asarray(rows, dtype=np.int64))
+    D = np.zeros((len(rows) + 1, inn + 1), dtype=np.float32)
+    D[:-1, :inn] = weight[rows]
+    D[:-1, inn] = 0 if bias is None else np.asarray(bias, dtype=np.float32)[rows]
+    D[-1, inn] = 1
+    (r, c) = np.nonzero(D)
+    grow = np.concatenate([rows, [out]])[r]
+    return csr_from_coo((out + 1, inn + 1), grow, c, D[r, c])
+
+
+def key_compile_rows(A, rows, W, Ainv):
+    """Rows `rows` of W_hat = A.dot(W).dot(Ainv): the same two csr_matmat products with A restricted to those rows
+    (a row of a product depends only on that row of the left factor).  W may be a row band: rows of W that
+    A[rows, :] does not touch are never read."""
+    rows = np.asarray(rows, dtype=np.int64)
+    if A is None:
+        counts = np.diff(W.indptr)[rows]
+        indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        take = np.concatenate([np.arange(W.indptr[r], W.indptr[r + 1]) for r in rows] + [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+        T = csr((len(rows), W.shape[1]), indptr, W.indices[take], W.data[take])
+    else:
+        counts = np.diff(A.indptr)[rows]
+        indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        take = np.concatenate([np.arange(A.indptr[r], A.indptr[r + 1]) for r in rows] + [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+        T = matmat(csr((len(rows), A.shape[1]), indptr, A.indices[take], A.data[take]), W)
+    return matmat(T, Ainv)
 
 
 def toeplitz_avgpool2d(inshape, kernel_size, stride):

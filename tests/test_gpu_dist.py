@@ -94,3 +94,29 @@ def test_sharded_model_world1_general_keys():
     y = m.forward(xc).reshape(64, -1).cpu().numpy()
     assert np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)
     assert np.allclose(y, _net()(x).detach().numpy(), atol=2e-4)
+
+
+@pytest.mark.parametrize('photometric', ['uniform_random_bias', 'uniform_random_affine', 'uniform_random_gain'])
+def test_row_shard_with_bias_keys_equals_rows_of_the_full_compile(photometric):
+    """a row shard compiled with a gathered column layout (col_remap) must carry the input key's bias
+    column.  One GPU is enough: shard rows + remapped columns of W_hat against the same rows of the unsharded compile."""
+    from keynet_b200 import system, sparse
+    rs = np.random.RandomState(0)
+    np.random.seed(1)
+    (A, _) = system.keygen((16, 14, 14), 'permutation', 'identity', photometric, 'identity', beta=1.0, gamma=1.0)
+    (_, Ainv) = system.keygen((6, 14, 14), 'permutation', 'identity', photometric, 'identity', beta=1.0, gamma=1.0)
+    f = rs.randn(16, 6, 3, 3).astype(np.float32); b = rs.randn(16).astype(np.float32)
+    full = sparse.keyed_toeplitz_conv2d((6, 14, 14), f, b, 1, A, Ainv, build_groups=False)
+    (R, K) = full.shape
+    rows = np.sort(rs.permutation(R - 1)[:500])
+    n_phys = K + 37
+    remap = np.concatenate([rs.permutation(n_phys - 1)[:K - 1], [n_phys - 1]]).astype(np.int64)       # homogeneous coordinate stays last
+    shard = sparse.keyed_toeplitz_conv2d((6, 14, 14), f, b, 1, A, Ainv, rows=rows, build_groups=False, col_remap=remap, n_cols_phys=n_phys)
+    assert shard.shape == (len(rows), n_phys)
+    D = full.todense()[rows]
+    S = shard.todense()
+    E = np.zeros_like(S)
+    E[:, remap] = D
+    assert np.array_equal(E.view(np.uint32), S.view(np.uint32))
+    if photometric != 'uniform_random_gain':
+        assert np.count_nonzero(S[:, -1]) > 0.9 * len(rows)            # the bias column is really there

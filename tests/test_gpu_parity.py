@@ -30,7 +30,7 @@ def _assert_bit_exact(W, shape, indptr, indices, data, what=''):
 
 def _close(a, b, rtol=RTOL):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    atol = 1e-5 * max(1.0, float(np.abs(b).max()) if b.size else 1.0)
+    atol = 1e-5 * (float(np.abs(b).max()) if b.size else 1.0)          # rtol 1e-4, atol 1e-5 * max|y| (no floor)
     return np.allclose(a, b, rtol=rtol, atol=atol)
 
 

@@ -58,3 +58,14 @@ def test_vgg16_permutation_keynet_single_gpu():
     assert scale > 0.05 and np.std(yp, axis=0).max() > 1e-3 * scale             # logits are input dependent
     assert np.allclose(y, yp, atol=1e-3 * max(1.0, scale)), (np.abs(y - yp).max(), scale)
     assert np.array_equal(y.argmax(1), yp.argmax(1))
+    # the benchmarked batch (256: tcgen05 kernels, two batch tiles) through the engine the bench uses
+    from keynet_b200 import engine
+    N = 256
+    plan = engine.ForwardPlan(sensor, knet, N, use_graph=False)
+    x = torch.randn(N, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = plan.run_device(x.cuda()).cpu().numpy()
+    with torch.no_grad():
+        yp = torch.cat([plain(x[i:i + 64].cuda()) for i in range(0, N, 64)]).cpu().numpy()
+    scale = np.abs(yp).max()
+    assert np.allclose(y, yp, atol=1e-3 * max(1.0, scale)), (np.abs(y - yp).max(), scale)
+    assert np.array_equal(y.argmax(1), yp.argmax(1))
