@@ -62,15 +62,26 @@ def he_weights(net, seed):
     """He-uniform weights (bound sqrt(6/fan_in)), small biases: the activation scale survives 16 ReLU layers, so the VGG16
     logits depend on the input and an argmax comparison means something (SURVEY.md 7 / cfg 4)."""
     import torch
-    rs = np.random.RandomState(seed)
+    rg = np.random.Generator(np.random.PCG64(seed))
     with torch.no_grad():
         for (name, p) in net.named_parameters():
-            if p.ndim > 1:
-                bound = np.sqrt(6.0 / int(np.prod(p.shape[1:])))
-                p.copy_(torch.from_numpy(rs.uniform(-bound, bound, size=tuple(p.shape)).astype(np.float32)))
-            else:
-                p.copy_(torch.from_numpy(rs.uniform(-0.1, 0.1, size=tuple(p.shape)).astype(np.float32)))
+            bound = np.float32(np.sqrt(6.0 / int(np.prod(p.shape[1:]))) if p.ndim > 1 else 0.1)
+            p.copy_(torch.from_numpy((rg.random(size=tuple(p.shape), dtype=np.float32) * (2 * bound) - bound).astype(np.float32)))
     return net
+
+
+class _no_default_init(object):
+    """Skip torch's own parameter initialisation while a net is constructed (138 M parameters that he_weights overwrites)."""
+
+    def __enter__(self):
+        import torch
+        self.saved = (torch.nn.Linear.reset_parameters, torch.nn.modules.conv._ConvNd.reset_parameters)
+        torch.nn.Linear.reset_parameters = lambda m: None
+        torch.nn.modules.conv._ConvNd.reset_parameters = lambda m: None
+
+    def __exit__(self, *a):
+        import torch
+        (torch.nn.Linear.reset_parameters, torch.nn.modules.conv._ConvNd.reset_parameters) = self.saved
 
 
 def workload(name):
@@ -83,7 +94,9 @@ def workload(name):
         return dict(name='lenet', net=numpy_weights(nets.LeNet_AvgPool(), 0).eval(), inshape=(1, 28, 28), keys=dict(global_geometric='permutation'),
                     label='LeNet_AvgPool 1x28x28, PermutationKeynet (BASELINE configs[0])')
     if name == 'vgg16':
-        return dict(name='vgg16', net=he_weights(nets.VGG16(), 0).eval(), inshape=(3, 224, 224), keys=dict(global_geometric='permutation'),
+        with _no_default_init():
+            net = nets.VGG16()
+        return dict(name='vgg16', net=he_weights(net, 0).eval(), inshape=(3, 224, 224), keys=dict(global_geometric='permutation'),
                     label='VGG16 3x224x224, PermutationKeynet (BASELINE metric / configs[3]: 15.0 G stored non-zeros = 120 GB as CSR)')
     raise ValueError(name)
 
@@ -484,7 +497,7 @@ def check_plan_against_oracle(plan, layers, n=64):
     """Small networks: the first n images of the timed batch through the oracle's csr_matvecs chain on the same compiled CSR."""
     from oracle import keynet_oracle as ko
     n = min(n, plan.N)
-    x = ko.affine_to_linear(plan.images[:n].detach().cpu().numpy())
+    x = ko.affine_to_linear(plan.images[:n].detach().cpu().numpy().reshape((n,) + tuple(plan.sensor._inshape[1:])))
     ref = ko.linear_to_affine(ko.keyed_forward(layers, x, threads=host_threads()))
     got = plan.logits[:n].detach().cpu().numpy()
     (frac_bad, rel) = _close_frac(got, ref)
@@ -895,7 +908,10 @@ def main():
         torch.cuda.empty_cache()
         extra = {}
         for (nm, b, sc) in (('lenet', LENET_BATCH, 'weak'), ('acn', max(128, ACN_BATCH // world), 'strong')):
-            r = bench_replicas(nm, b, max(K, 10), args.warmup, rank, world, local_rank, want_cpu=want_cpu, cpu_budget_s=6.0, scaling=sc)
+            try:
+                r = bench_replicas(nm, b, max(K, 10), args.warmup, rank, world, local_rank, want_cpu=want_cpu, cpu_budget_s=6.0, scaling=sc)
+            except Exception as e:             # a failing sub-record must not take the headline line with it (all ranks fail alike)
+                r = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
             torch.cuda.empty_cache()
             if rank == 0:
                 extra[nm] = r

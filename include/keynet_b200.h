@@ -205,6 +205,35 @@ int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, const floa
                        const float *row_bias, const float *col_bias, int64_t n_cols_in, int32_t keep_zeros,
                        const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
 
+/* ---- fused key compile of a conv / linear layer (csrc/keyedconv.cu) ------------------------------------------------
+ * W_hat = A . toeplitz(conv2d) . Ainv for monomial keys WITHOUT materialising the un-keyed Toeplitz matrix: replaces
+ * keynet/sparse.py:163-203 (sparse_toeplitz_conv2d) + the two SpGEMMs of keynet/layer.py:35 (and, as a 1x1 convolution
+ * on a 1x1 image, keynet/torch.py:80-89 + keynet/layer.py:69-70 for nn.Linear) in one pass with one column sort per
+ * output pixel -- all M rows of a pixel share their column set.
+ *   pix[n_groups]        output pixels to compile (ku*Vo + kv), NULL = all Uo*Vo pixels in raster order
+ *   row_of_src[R_src+1]  compiled row of every Toeplitz row s = m*Uo*Vo + pixel (last entry: the homogeneous row); < 0 =
+ *                        not held by this shard; NULL = identity (no output key, not sharded)
+ *   col_map[K_src+1]     new column of every source column (input key / gathered layout); NULL = identity
+ *   row_scale (per compiled row), col_scale (per source column): gains of A and Ainv; NULL = 1
+ * Values: fl32(fl32(row_scale*w)*col_scale), exact zeros dropped unless keep_zeros; columns ascending.  Weights must be
+ * the offset-rounded ones (keynet/sparse.py:184-187).  Two phase: count -> kn_exclusive_scan_i64 -> fill.
+ * Returns KN_ERR_UNSUPPORTED when C*P*Q+1 exceeds the shared-memory sort (8192): use the two-kernel path then. */
+int kn_keyed_conv2d_count(const kn_conv2d_desc *desc, const float *weight, const float *bias, const int32_t *pix, int64_t n_groups,
+                          const int32_t *row_of_src, const float *row_scale, const float *col_scale, int32_t keep_zeros,
+                          int64_t *row_nnz, void *stream);
+int kn_keyed_conv2d_fill(const kn_conv2d_desc *desc, const float *weight, const float *bias, const int32_t *pix, int64_t n_groups,
+                         const int32_t *row_of_src, const int32_t *col_map, const float *row_scale, const float *col_scale, int32_t keep_zeros,
+                         const int64_t *out_indptr, int32_t *out_indices, float *out_data, void *stream);
+/* The pattern-group execution format (below) of the same keyed layer straight from the geometry, no CSR involved:
+ *   kn_conv2d_groups_index   rows[g][M], cols[g][K_pad] (Toeplitz tap order, padding repeats the first column), group_k[g]
+ *   kn_conv2d_groups_values  vals[b][M][K_pad] for the pixels block_pix[b]: one block per pixel with gain keys, one block per
+ *                            border class (which taps are in bounds) with permutation-only keys -- the unique tiles of
+ *                            keynet/sparse.py:553-568,690-779 by construction. */
+int kn_conv2d_groups_index(const kn_conv2d_desc *desc, const int32_t *pix, int64_t n_groups, const int32_t *row_of_src, const int32_t *col_map,
+                           int32_t K_pad, int32_t *rows, int32_t *cols, int32_t *group_k, void *stream);
+int kn_conv2d_groups_values(const kn_conv2d_desc *desc, const float *weight, const float *bias, const int32_t *block_pix, int64_t n_blocks,
+                            const int32_t *row_of_src, const float *row_scale, const float *col_scale, int32_t K_pad, float *vals, void *stream);
+
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left
  * for explicit matrices, e.g. sensor keys / ReLU keys, keynet/layer.py:46). */
 int kn_csr_gather_rows_count(const int64_t *indptr, const int64_t *row_ids, int64_t n_rows, int64_t *row_nnz, void *stream);

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('KEYNET_B200_LIB', os.path.join(_HERE, 'lib', 'libkeynet_b200.so'))
 
 KN_SPMM_RELU = 1
+KN_ERR_UNSUPPORTED = -3
 
 # every symbol include/keynet_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
@@ -20,6 +21,7 @@ SYMBOLS = [
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
     'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
+    'kn_keyed_conv2d_count', 'kn_keyed_conv2d_fill', 'kn_conv2d_groups_index', 'kn_conv2d_groups_values',
     'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact', 'kn_encrypt_monomial_t', 'kn_splitk_reduce_f32',
 ]
 
@@ -79,6 +81,10 @@ def lib():
         'kn_linear_fill': [vp, vp, i64, i64, vp, i64, vp, vp, vp, vp],
         'kn_keycompile_count': [vp, vp, vp, i64, vp, vp, vp, vp, i64, ctypes.c_int32, vp, vp],
         'kn_keycompile_fill': [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, ctypes.c_int32, vp, vp, vp, vp],
+        'kn_keyed_conv2d_count': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, ctypes.c_int32, vp, vp],
+        'kn_keyed_conv2d_fill': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, vp, ctypes.c_int32, vp, vp, vp, vp],
+        'kn_conv2d_groups_index': [ctypes.POINTER(kn_conv2d_desc), vp, i64, vp, vp, ctypes.c_int32, vp, vp, vp, vp],
+        'kn_conv2d_groups_values': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, ctypes.c_int32, vp, vp],
         'kn_csr_gather_rows_count': [vp, vp, i64, vp, vp],
         'kn_csr_gather_rows_fill': [vp, vp, vp, vp, i64, vp, vp, vp, vp],
         'kn_affine_to_linear_t': [vp, i64, i64, vp, i64, vp],

@@ -30,6 +30,21 @@ void kn_set_error(const char *fmt, ...);
 
 #define KN_CHECK_LAUNCH() KN_CUDA(cudaGetLastError())
 
+// cudaFuncSetAttribute belongs to the function ON ONE DEVICE: a process that drives several GPUs must set it on each.
+// KN_ONCE_PER_DEVICE { ... } runs its body the first time the enclosing call site (one per template instantiation) is
+// reached with a given current device.
+struct KnOncePerDevice {
+    bool done[64] = {false};
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+#define KN_ONCE_PER_DEVICE static KnOncePerDevice kn_once_; if (kn_once_.first())
+
 static inline int64_t kn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Output replication for the fused SpMM + all-gather (K5): when n > 0 every epilogue stores its rows to all n buffers

@@ -107,6 +107,44 @@ keycompile_count_bias_kernel(const int64_t *__restrict__ indptr, const int32_t *
     }
 }
 
+// Rows with at most 32 entries (pooling layers: k*k taps; permutation / gain matrices: one entry): one WARP per row, the
+// entries sorted by ranking -- every lane counts the kept entries with a smaller new column through 32 shuffles.  (One CTA
+// per row, as below, spends 256 threads and a dozen barriers on 9 entries: VGG16's pooling layers have 1.5 M such rows.)
+constexpr int kShortRow = 32;
+
+__global__ void __launch_bounds__(kThreads)
+keycompile_fill_short_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                             int64_t n_rows, const int32_t *__restrict__ col_map,
+                             const float *__restrict__ row_scale, const float *__restrict__ col_scale, int keep_zeros,
+                             const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = kThreads / 32;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + warp; r < n_rows; r += (int64_t)gridDim.x * wpb) {
+        const int64_t beg = indptr[r];
+        const int n = (int)(indptr[r + 1] - beg);
+        if (n > kShortRow || n == 0) continue;               // warp-uniform; long rows belong to the CTA kernel
+        const int64_t obeg = out_indptr[r];
+        int32_t cn = 0x7fffffff;
+        float v = 0.0f;
+        bool keep = false;
+        if (lane < n) {
+            const int32_t c = indices[beg + lane];
+            v = keyed_value(data[beg + lane], row_scale, col_scale, r, c);
+            keep = keep_zeros || v != 0.0f;
+            cn = col_map ? col_map[c] : c;
+        }
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < kShortRow; j++) {
+            const int32_t cj = __shfl_sync(0xffffffffu, cn, j);
+            const int kj = __shfl_sync(0xffffffffu, keep ? 1 : 0, j);
+            rank += (kj && cj < cn) ? 1 : 0;
+        }
+        if (keep) { out_indices[obeg + rank] = cn; out_data[obeg + rank] = v; }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
                        int64_t n_rows, int64_t n_cols, const int32_t *__restrict__ col_map,
@@ -126,6 +164,7 @@ keycompile_fill_kernel(const int64_t *__restrict__ indptr, const int32_t *__rest
         const int64_t obeg = out_indptr[r];
         int64_t n_out = out_indptr[r + 1] - obeg;
         if (n_out == 0) continue;                               // block-uniform
+        if (!biased && end - beg <= kShortRow) continue;        // written by keycompile_fill_short_kernel
         if (biased) {
             // the last-column entry is a row reduction; it is the largest column, so it goes straight to the row's end
             const float last = biased_last_value(indices, data, beg, end, r, last_in, row_scale, row_bias, col_bias, s_red);
@@ -259,10 +298,13 @@ KN_API int kn_keycompile_fill(const int64_t *indptr, const int32_t *indices, con
     KN_REQUIRE(indptr && indices && data && out_indptr && out_indices && out_data, "keycompile: null pointer");
     KN_REQUIRE(out_indices != indices && out_data != data, "keycompile: in-place compile is not supported");
     const size_t smem = (size_t)kSmemCap * (sizeof(int32_t) + sizeof(float));
-    static bool configured = false;   // per process; attribute is sticky per function
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(keycompile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    }
+    if (!(row_bias || col_bias)) {
+        keycompile_fill_short_kernel<<<row_grid(n_rows, kThreads / 32), kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, col_map, row_scale, col_scale, keep_zeros,
+                                                                                                     out_indptr, out_indices, out_data);
+        KN_CHECK_LAUNCH();
     }
     keycompile_fill_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, n_rows, n_cols, col_map, row_scale, col_scale, row_bias, col_bias,
                                                                                          (row_bias || col_bias) ? (int32_t)(n_cols_in - 1) : -1, keep_zeros,

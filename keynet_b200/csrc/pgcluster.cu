@@ -128,11 +128,9 @@ int launch_cluster(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm_cg: grid too large");
     const size_t smem = (size_t)u_max * TN * sizeof(float) + (size_t)g_max * K_pad * sizeof(int32_t);
     KN_REQUIRE(smem <= (size_t)KN_CG_MAX_UNION * TN * sizeof(float), "spmm_cg: staged tile + index table of %zu bytes do not fit", smem);
-    static bool configured = false;
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(pg_cluster_kernel<GM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KN_CG_MAX_UNION * TN * (int)sizeof(float)));
         KN_CUDA(cudaFuncSetAttribute(pg_cluster_kernel<GM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KN_CG_MAX_UNION * TN * (int)sizeof(float)));
-        configured = true;
     }
     if (relu) pg_cluster_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, n_chunks, gm_total, X, ldx, Y, ldy, n_vecs, kn_current_peers());
     else      pg_cluster_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(cl_gptr, cl_uptr, ucols, rows, lidx, valsT, group_k, block_of, n_clusters, G, K_pad, u_max, n_chunks, gm_total, X, ldx, Y, ldy, n_vecs, kn_current_peers());

@@ -333,11 +333,9 @@ int launch_small(const int32_t *rows, const int32_t *cols, const float *vals, co
     const int64_t n_items = n_groups * n_supers, gx = kn_cdiv(n_items, kThreads / 32);
     KN_REQUIRE(gx <= 0x7fffffffLL, "spmm_pg(small): grid too large");
     const size_t smem = (size_t)(kThreads / 32) * K_pad * (GM + 1) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(pg_small_kernel<GM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_small_kernel<GM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
     }
     if (relu) pg_small_kernel<GM, true><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs, kn_current_peers());
     else      pg_small_kernel<GM, false><<<(unsigned)gx, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, n_supers, tiles_per_super, X, ldx, Y, ldy, n_vecs, kn_current_peers());
@@ -354,11 +352,9 @@ int launch_pg(const int32_t *rows, const int32_t *cols, const float *vals, const
     const int tiles_per_group = (G + TM - 1) / TM;
     const int64_t gx = n_groups * tiles_per_group, gy = kn_cdiv(n_vecs, TN);
     KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg: grid too large");
-    static bool configured = false;
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KN_CUDA(cudaFuncSetAttribute(pg_simt_kernel<RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     dim3 grid((unsigned)(gx * gy));
     if (relu) pg_simt_kernel<RW, true><<<grid, kThreads, smem, s>>>(rows, cols, vals, group_k, block_of, n_groups, G, K_pad, tiles_per_group, gx, gy, X, ldx, Y, ldy, n_vecs, kn_current_peers());

@@ -440,13 +440,11 @@ int launch_tc(const CUtensorMap *maps, const int32_t *rows, const int32_t *cols,
     const size_t smem = (size_t)n_b * stage + (size_t)K_pad * 4 + 1024 + 512;
     const int64_t gx = n_groups * chunks_per_group, gy = kn_cdiv(n_vecs, BM * NB);
     KN_REQUIRE(gx * gy <= 0x7fffffffLL, "spmm_pg_tc: grid too large");
-    static bool configured = false;
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, true, DUAL, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_tc_kernel<NB, false, DUAL, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     const CUtensorMap *m = maps + (CS > 1 ? 2 : 0);              // maps[2..3]: boxes of Gp/2 rows for the multicast halves
     cudaLaunchConfig_t cfg = {};

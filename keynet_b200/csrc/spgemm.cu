@@ -159,10 +159,8 @@ KN_API int kn_spgemm_rows(const int64_t *a_indptr, const int32_t *a_indices, con
     if (n_rows == 0) return KN_OK;
     KN_REQUIRE(a_indptr && b_indptr && tmp_ptr && row_nnz, "spgemm_rows: null pointer");
     const size_t smem = (size_t)kSmemCap * (sizeof(int32_t) + sizeof(float));
-    static bool configured = false;
-    if (!configured) {
+    KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     spgemm_rows_kernel<<<row_grid(n_rows, 1), kThreads, smem, (cudaStream_t)stream>>>(a_indptr, a_indices, a_data, n_rows, b_indptr, b_indices, b_data,
                                                                                         tmp_ptr, tmp_indices, tmp_data, row_nnz);

@@ -24,10 +24,12 @@ class FusedReLU(nn.Module):
 
 
 class KeyedLayer(nn.Module):
-    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None, col_remap=None, n_cols_phys=None, keep_csr=True):
+    def __init__(self, module, inshape, outshape, A, Ainv, tileshape=None, rows=None, col_remap=None, n_cols_phys=None, keep_csr=True, build_groups=True):
         """module: nn.Conv2d | nn.AvgPool2d | nn.Linear | nn.ReLU; A / Ainv: MonomialKey (A may be None for the
         last layer); rows=(r0, r1) or an index array: build and hold only those rows of W_hat (row shard);
-        col_remap / n_cols_phys: physical position of every canonical input column (gathered layout, dist.py)."""
+        col_remap / n_cols_phys: physical position of every canonical input column (gathered layout, dist.py);
+        keep_csr=False: conv / linear layers are built as pattern groups only and never exist as a CSR (VGG16 scale);
+        build_groups=False: canonical CSR only (key-compile sweep, parity / export)."""
         super(KeyedLayer, self).__init__()
         self._layertype = str(type(module))
         self._inshape = inshape
@@ -35,6 +37,8 @@ class KeyedLayer(nn.Module):
         self._tileshape = tileshape
         self._fused_relu = False
         self._rows = rows
+        self._build_groups = bool(build_groups)
+        want_csr = bool(keep_csr) or tileshape is not None or not build_groups
         assert A is None or isinstance(A, (MonomialKey, SparseKey)), 'A must be a key (MonomialKey / SparseKey)'
         assert isinstance(Ainv, (MonomialKey, SparseKey)), 'Ainv must be a key (MonomialKey / SparseKey)'
         t0 = time.time()
@@ -57,7 +61,8 @@ class KeyedLayer(nn.Module):
             stride = module.stride[0]
             self._repr = 'Conv2d: in_channels=%d, out_channels=%d, kernel_size=%s, stride=%s' % (module.in_channels, module.out_channels, str(module.kernel_size), str(stride))
             bias = module.bias.detach().cpu().numpy() if module.bias is not None else np.zeros(module.out_channels, dtype=np.float32)
-            self.W = sparse.keyed_toeplitz_conv2d(inshape, module.weight.detach().cpu().numpy(), bias, stride, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys)
+            self.W = sparse.keyed_toeplitz_conv2d(inshape, module.weight.detach().cpu().numpy(), bias, stride, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys,
+                                                  build_groups=build_groups, want_csr=want_csr)
 
         elif isinstance(module, nn.ReLU):
             # explicit keyed ReLU (only after a batchnorm merge, keynet/system.py:97-99): W = A . Ainv, then ReLU
@@ -79,7 +84,8 @@ class KeyedLayer(nn.Module):
 
         elif isinstance(module, nn.Linear):
             self._repr = 'Linear: in_features=%d, out_features=%d' % (module.in_features, module.out_features)
-            self.W = sparse.keyed_linear(module.weight.detach(), module.bias.detach() if module.bias is not None else None, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys)
+            self.W = sparse.keyed_linear(module.weight.detach(), module.bias.detach() if module.bias is not None else None, A, Ainv, rows=rows, col_remap=col_remap, n_cols_phys=n_cols_phys,
+                                         build_groups=build_groups, want_csr=want_csr)
 
         elif isinstance(module, nn.BatchNorm2d):
             raise ValueError('batchnorm layer should be named "mylayer_bn" for batchnorm of "mylayer" and should come right before "mylayer" to merge keyed layers')
@@ -120,7 +126,7 @@ class KeyedLayer(nn.Module):
         self.W = W.matmul(Ainv)
 
     def _finish(self, module, inshape, outshape, tileshape, keep_csr, t0):
-        if tileshape is None:
+        if tileshape is None and self._build_groups:
             self.W.optimize()          # pattern-grouped execution format for batched forward (no-op if the builder made it)
         if tileshape is not None:
             from .tiled import tile_keyed_layer

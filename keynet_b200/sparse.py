@@ -66,6 +66,12 @@ class MonomialKey(object):
     def is_identity(self):
         return self.is_unpermuted() and self.is_unscaled() and self.bias is None
 
+    def _identity(self):
+        """is_identity(), evaluated once (keys are immutable once built)."""
+        if getattr(self, '_ident', None) is None:
+            self._ident = self.is_identity()
+        return self._ident
+
     @property
     def nnz(self):
         return len(self.perm)
@@ -75,6 +81,12 @@ class MonomialKey(object):
         """self . other.  other: MonomialKey -> MonomialKey; SparseMatrix -> SparseMatrix (row gather + scale)."""
         if isinstance(other, MonomialKey):
             assert self.shape[1] == other.shape[0], 'non-conformal keys %s, %s' % (str(self.shape), str(other.shape))
+            # products with the identity are exact in fp32 (1*x = x): most factors of keygen's A = C^-1.p.g.P.G.C are identities
+            if self.bias is None and other.bias is None:
+                if other._identity():
+                    return self
+                if self._identity():
+                    return other
             bias = None
             if self.bias is not None or other.bias is not None:
                 # row r of the product: scale_a[r] * (row perm_a[r] of B) + bias_a[r] * e_last; scipy accumulates the
@@ -638,6 +650,8 @@ class SparseMatrix(object):
         """Free the canonical CSR and keep only the pattern-grouped execution format (VGG16-scale layers: 120 GB of
         CSR vs < 1 GB of unique value blocks + gather lists).  The matrix can no longer be exported or row-sliced."""
         assert self._pg is not None, 'drop_csr() needs the pattern-grouped format'
+        if self._data is None:
+            return self                       # built without a CSR in the first place (direct pattern groups)
         self._nnz = self.nnz()
         self._device = self._data.device
         (self._indptr, self._indices, self._data) = (None, None, None)
@@ -813,6 +827,16 @@ def tensor_cores_enabled(flag=None):
 
 
 _CLUSTERS = [True]
+_DIRECT = [os.environ.get('KEYNET_B200_DIRECT_COMPILE', '1') != '0']
+
+
+def direct_compile_enabled(flag=None):
+    """Switch for the fused key compile of conv / linear layers (csrc/keyedconv.cu); off = Toeplitz CSR + per-row key compile +
+    pattern hashing (the two-kernel path, kept for keys with bias columns and for A/B tests)."""
+    if flag is not None:
+        _DIRECT[0] = bool(flag)
+    return _DIRECT[0]
+
 
 
 def clusters_enabled(flag=None):
@@ -965,17 +989,7 @@ class PatternGroups(object):
                     (cols, vals, block_of) = _dedup_value_blocks(cols, vals, group_k, ng, int(G), K_pad)
                 cls = dict(G=int(G), K_pad=K_pad, n_groups=ng, rows=rows64.to(torch.int32), cols=cols, vals=vals, tc=None,
                            group_k=group_k, block_of=block_of, n_blocks=ng if block_of is None else int(vals.numel() // (int(G) * K_pad)))
-                if int(G) >= PatternGroups.TC_MIN_G and PatternGroups.TC_MIN_K <= K_pad <= PatternGroups.TC_MAX_K and tensor_cores_enabled():
-                    # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
-                    (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
-                    check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
-                    maps = ctypes.create_string_buffer(4 * 128)
-                    check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * int(G), int(G), K_pad, maps))
-                    cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
-                if cls['tc'] is not None and ng == 1 and Kl[b0] >= PatternGroups.SPLITK_MIN_K:
-                    cls['splitk'] = PatternGroups._split_k(cls, int(Kl[b0]))
-                if cid is not None and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
-                    cls['cg'] = PatternGroups._cluster(cls, cid, C)
+                PatternGroups._finish_class(cls, int(Kl[b0]), cid, C)
                 pg.classes.append(cls)
                 in_group[rows64] = True
                 pg.grouped_rows += ng * int(G)
@@ -992,6 +1006,25 @@ class PatternGroups(object):
         if len(pg.classes) == 0:
             return None
         return pg
+
+    @staticmethod
+    def _finish_class(cls, K_max, cid, n_cols):
+        """Execution extras of one class: TF32 hi/lo planes + TMA descriptors for the tensor-core kernel, K slices for a
+        single tall group (dense fc layers), the clustered form for short reductions (cid: cluster id per group, sorted)."""
+        L = _native.lib()
+        (G, K_pad, ng, vals) = (cls['G'], cls['K_pad'], cls['n_groups'], cls['vals'])
+        if G >= PatternGroups.TC_MIN_G and PatternGroups.TC_MIN_K <= K_pad <= PatternGroups.TC_MAX_K and tensor_cores_enabled():
+            # tensor-core operands: hi/lo TF32 split of the value blocks + TMA descriptors (csrc/pgroup_tc.cu)
+            (vhi, vlo) = (torch.empty_like(vals), torch.empty_like(vals))
+            check(L.kn_pg_tc_split(ptr(vals), vals.numel(), ptr(vhi), ptr(vlo), stream_ptr()))
+            maps = ctypes.create_string_buffer(4 * 128)
+            check(L.kn_pg_tc_tensormaps(ptr(vhi), ptr(vlo), cls['n_blocks'] * G, G, K_pad, maps))
+            cls['tc'] = dict(hi=vhi, lo=vlo, maps=maps)
+        if cls['tc'] is not None and ng == 1 and K_max >= PatternGroups.SPLITK_MIN_K:
+            cls['splitk'] = PatternGroups._split_k(cls, int(K_max))
+        if cid is not None and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
+            cls['cg'] = PatternGroups._cluster(cls, cid, n_cols)
+        return cls
 
     SPLITK_MAX_BATCH = 1024  # wider batches already give every SM a batch tile
     SPLITK_MIN_K = 2048      # a single group with a reduction at least this long is cut into K slices (dense fc layers)
@@ -1241,12 +1274,165 @@ def _conv_weights_rounded(inshape, f, bias, stride):
     return (fq, bq, (C, U, V, M, P, Q))
 
 
-def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True, col_remap=None, n_cols_phys=None):
+def _axis_class(U, k, stride):
+    """Per output position along one axis: (first in-bounds tap offset + h) * (k+1) + number of in-bounds taps."""
+    h = (k - 1) // 2
+    u = np.arange(0, U, stride)
+    lo = np.maximum(-h, -u)
+    hi = np.minimum(h, U - 1 - u)
+    return ((lo + h) * (k + 1) + np.maximum(0, hi - lo + 1)).astype(np.int64)
+
+
+def _keyed_conv_direct(geom, wq, bq, A, Ainv, rows, col_remap, n_cols_phys, want_csr, build_groups, dev, clustered=False):
+    """Fused compile of a conv / linear layer under monomial keys (csrc/keyedconv.cu): canonical CSR written in one pass
+    with one column sort per output pixel (want_csr) and / or the pattern-group execution format straight from the
+    geometry (build_groups).  Returns a SparseMatrix, or None when the keys / the shard do not fit this route (bias
+    columns, a shard that cuts through a pixel's channel rows): the caller then takes the two-kernel path."""
+    (C, U, V, M, P, Q, stride, has_bias) = geom
+    L = _native.lib()
+    if (A is not None and A.bias is not None) or Ainv.bias is not None:
+        return None
+    (Uo, Vo) = (U // stride, V // stride)
+    UoVo = Uo * Vo
+    R_src = M * UoVo + 1
+    K_src = C * U * V + 1
+    desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1 if has_bias else 0)
+    # ---- which compiled row holds which Toeplitz row
+    if rows is None:
+        (n, sel) = (R_src, slice(0, R_src))
+        src = None if (A is None or A.is_unpermuted()) else A.perm
+    elif isinstance(rows, tuple):
+        sel = slice(int(rows[0]), int(rows[1]))
+        n = sel.stop - sel.start
+        src = (np.arange(sel.start, sel.stop, dtype=np.int64) if A is None else A.perm[sel])
+    else:
+        sel = np.ascontiguousarray(rows, dtype=np.int64)
+        n = len(sel)
+        src = sel if A is None else A.perm[sel]
+    if n == 0:
+        return None
+    if src is None:
+        (row_of_src, pix, pix_np, n_groups) = (None, None, np.arange(UoVo, dtype=np.int64), UoVo)
+    else:
+        inv = np.full(R_src, -1, dtype=np.int32)
+        inv[src] = np.arange(n, dtype=np.int32)
+        main = src[src < R_src - 1]
+        pix_np = np.unique(main % UoVo) if rows is not None else np.arange(UoVo, dtype=np.int64)
+        if len(main) != M * len(pix_np):
+            return None                                  # the shard cuts through a pixel's channel rows
+        row_of_src = torch.from_numpy(inv).to(dev)
+        n_groups = len(pix_np)
+        pix = None if n_groups == UoVo else torch.from_numpy(pix_np.astype(np.int32)).to(dev)
+    # ---- keys as vectors
+    (AinvP, Kp) = _remapped(Ainv, col_remap, n_cols_phys)
+    assert Ainv.shape[0] == K_src
+    col_map = None
+    if AinvP.shape[0] != AinvP.shape[1] or not AinvP.is_unpermuted():
+        col_map = torch.from_numpy(AinvP.perm.astype(np.int32)).to(dev)
+    col_scale = None if Ainv.is_unscaled() else torch.from_numpy(Ainv.scale).to(dev)
+    row_scale = None
+    if A is not None and not A.is_unscaled():
+        row_scale = torch.from_numpy(np.ascontiguousarray(A.scale[sel])).to(dev)
+    w = torch.from_numpy(np.ascontiguousarray(wq, dtype=np.float32)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(bq, dtype=np.float32)).to(dev) if has_bias else None
+    # ---- canonical CSR (or only its row counts: nnz() of a layer that never holds a CSR)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    check(L.kn_keyed_conv2d_count(desc, ptr(w), ptr(b), ptr(pix), n_groups, ptr(row_of_src), ptr(row_scale), ptr(col_scale), 0, ptr(indptr[1:]), stream_ptr()))
+    _scan_counts_inplace(indptr)
+    nnz = int(indptr[-1].item())
+    W = SparseMatrix()
+    W.shape = (n, Kp)
+    if want_csr:
+        indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+        data = torch.empty(nnz, dtype=torch.float32, device=dev)
+        if nnz > 0:
+            rc = L.kn_keyed_conv2d_fill(desc, ptr(w), ptr(b), ptr(pix), n_groups, ptr(row_of_src), ptr(col_map), ptr(row_scale), ptr(col_scale), 0,
+                                        ptr(indptr), ptr(indices), ptr(data), stream_ptr())
+            if rc == _native.KN_ERR_UNSUPPORTED:
+                return None                              # more taps per pixel than the shared-memory sort holds
+            check(rc)
+        (W._indptr, W._indices, W._data) = (indptr, indices, data)
+    else:
+        (W._nnz, W._device) = (nnz, dev)
+        del indptr
+    if not (build_groups and M >= 4 and nnz >= 4096 and n_groups > 0):
+        return W if want_csr else None
+    # ---- pattern groups: one per output pixel, one class per layer
+    K_pad = (C * P * Q + (1 if has_bias else 0) + 31) // 32 * 32
+    cid = None
+    if clustered and M <= PatternGroups.CG_MAX_G and K_pad <= PatternGroups.CG_KERNEL_MAX_K:
+        # groups stored tile by tile for the clustered kernel (csrc/pgcluster.cu): t x t output pixels whose union of taps
+        # fits its staging buffer
+        staged = lambda t: (((t - 1) * stride + P) ** 2 * C + 1) * 512 + t * t * K_pad * 4
+        t = 0
+        while t < max(Uo, Vo) and staged(t + 1) <= PatternGroups.CG_MAX_UNION * 512:
+            t += 1
+        if t > 0:
+            for dd in range(t, max(1, t // 2), -1):
+                if Uo % dd == 0 and Vo % dd == 0:
+                    t = dd
+                    break
+            tile = (pix_np // Vo // t) * (-(-Vo // t)) + (pix_np % Vo) // t
+            o = np.argsort(tile, kind='stable')
+            (pix_np, tile) = (pix_np[o], tile[o])
+            pix = torch.from_numpy(pix_np.astype(np.int32)).to(dev)
+            cid = torch.from_numpy(tile.astype(np.int64)).to(dev)
+    ng = n_groups
+    rows_t = torch.empty(ng * M, dtype=torch.int32, device=dev)
+    cols = torch.empty(ng * K_pad, dtype=torch.int32, device=dev)
+    group_k = torch.empty(ng, dtype=torch.int32, device=dev)
+    check(L.kn_conv2d_groups_index(desc, ptr(pix), ng, ptr(row_of_src), ptr(col_map), K_pad, ptr(rows_t), ptr(cols), ptr(group_k), stream_ptr()))
+    scaled = row_scale is not None or col_scale is not None
+    block_of = None
+    if scaled or ng == 1:
+        block_pix = pix if pix is not None else torch.arange(ng, dtype=torch.int32, device=dev)
+        n_blocks = ng
+    else:
+        # permutation-only keys: the value block depends only on which taps are in bounds
+        key = _axis_class(U, P, stride)[pix_np // Vo] * ((P + 1) * (P + 1) + 1) + _axis_class(V, Q, stride)[pix_np % Vo]
+        (_, first, inverse) = np.unique(key, return_index=True, return_inverse=True)
+        n_blocks = len(first)
+        block_pix = torch.from_numpy(pix_np[first].astype(np.int32)).to(dev)
+        block_of = torch.from_numpy(inverse.astype(np.int32)).to(dev)
+    vals = torch.empty(n_blocks * M * K_pad, dtype=torch.float32, device=dev)
+    check(L.kn_conv2d_groups_values(desc, ptr(w), ptr(b), ptr(block_pix), n_blocks, ptr(row_of_src), ptr(row_scale), ptr(col_scale), K_pad, ptr(vals), stream_ptr()))
+    pg = PatternGroups()
+    pg.shape = W.shape
+    cls = dict(G=M, K_pad=K_pad, n_groups=ng, rows=rows_t, cols=cols, vals=vals, tc=None, group_k=group_k, block_of=block_of, n_blocks=n_blocks)
+    PatternGroups._finish_class(cls, C * P * Q + (1 if has_bias else 0), cid, Kp)
+    pg.classes.append(cls)
+    pg.grouped_rows = ng * M
+    pg.padded_values = n_blocks * M * K_pad
+    # the homogeneous row e_last (one entry) is the only row outside the groups
+    r_h = (R_src - 1) if src is None else int(inv[R_src - 1])
+    if r_h >= 0:
+        v = np.float32(1.0)
+        if A is not None and not A.is_unscaled():
+            v = np.float32(A.scale[sel][r_h] * v)
+        if not Ainv.is_unscaled():
+            v = np.float32(v * Ainv.scale[K_src - 1])
+        if v != 0:
+            c_h = int(AinvP.perm[K_src - 1])
+            pg.rest = dict(n=1, indptr=torch.tensor([0, 1], dtype=torch.int64, device=dev), indices=torch.tensor([c_h], dtype=torch.int32, device=dev),
+                           data=torch.tensor([float(v)], dtype=torch.float32, device=dev), out_rows=torch.tensor([r_h], dtype=torch.int32, device=dev))
+    W._pg = pg
+    return W
+
+
+
+def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True, col_remap=None, n_cols_phys=None, want_csr=True):
     """W_hat = A . toeplitz(conv2d) . Ainv built on the GPU for monomial keys (keynet/layer.py:32-35).
 
-    rows=(r0, r1) builds only that row range of W_hat (row shard); indptr then has r1-r0+1 entries."""
+    rows=(r0, r1) builds only that row range of W_hat (row shard); indptr then has r1-r0+1 entries.
+    want_csr=False (with build_groups): only the pattern-group execution format is built -- the layer never exists as a
+    CSR (VGG16: 120 GB); nnz() still reports the reference's stored-entry count."""
     dev = _device()
     (fq, bq, (C, U, V, M, P, Q)) = _conv_weights_rounded(inshape, f, bias, stride)
+    if _DIRECT[0] and (A is None or isinstance(A, MonomialKey)) and isinstance(Ainv, MonomialKey):
+        clustered = M <= PatternGroups.CG_MAX_G and (C * P * Q + 1 + 31) // 32 * 32 <= PatternGroups.CG_KERNEL_MAX_K
+        W = _keyed_conv_direct((C, U, V, M, P, Q, int(stride), True), fq, bq, A, Ainv, rows, col_remap, n_cols_phys, want_csr, build_groups, dev, clustered=clustered)
+        if W is not None:
+            return W
     R = M * (U // stride) * (V // stride) + 1
     K = C * U * V + 1
     desc = kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1)
@@ -1346,12 +1532,23 @@ def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, c
     return W
 
 
-def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=None):
+def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=None, build_groups=True, want_csr=True):
     """W_hat = A . [[W, b],[0, 1]] . Ainv (keynet/layer.py:69-70)."""
     dev = _device()
     L = _native.lib()
     W = torch.as_tensor(weight).detach().to(device=dev, dtype=torch.float32).contiguous()
     (n_out, n_in) = W.shape
+    if _DIRECT[0] and (A is None or isinstance(A, MonomialKey)) and isinstance(Ainv, MonomialKey) and Ainv.bias is None and (A is None or A.bias is None):
+        # a linear layer is a 1x1 convolution on a 1x1 image: one output "pixel", one pattern group holding every row
+        wn = W.cpu().numpy()
+        bn = None if bias is None else torch.as_tensor(bias).detach().cpu().numpy().astype(np.float32)
+        fits = n_in + 1 <= 8192                      # taps per pixel the fused CSR writer sorts in shared memory
+        M_ = _keyed_conv_direct((int(n_in), 1, 1, int(n_out), 1, 1, 1, bn is not None), wn, bn, A, Ainv, rows, col_remap, n_cols_phys, want_csr and fits, build_groups, dev)
+        if M_ is not None and (fits or not want_csr):
+            return M_
+        pg = M_._pg if M_ is not None else None      # groups built directly, canonical CSR through the two-kernel path below
+    else:
+        pg = None
     b = torch.as_tensor(bias).detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
     (ids, sel) = _row_ids(A, n_out + 1, rows, dev)
     n = _n_selected(sel, n_out + 1)
@@ -1362,7 +1559,9 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
         lambda ip, ix, dt: check(L.kn_linear_fill(ptr(W), ptr(b), n_out, n_in, ptr(ids), n, ptr(ip), ptr(ix), ptr(dt), stream_ptr())),
         dev)
     csr = _keycompile(csr, n, n_in + 1, A, Ainv, dev, row_scale_slice=sel)
-    return SparseMatrix(((n, Kp), *csr), device=dev)
+    M_ = SparseMatrix(((n, Kp), *csr), device=dev)
+    M_._pg = pg
+    return M_
 
 
 def sparse_toeplitz_conv2d(inshape, f, bias=None, as_correlation=True, stride=1, format='csr'):
