@@ -351,146 +351,199 @@ def layergen(module, inshape, outshape, A, Ainv, tileshape=None, backend='b200',
     raise ValueError('invalid backend "%s"' % backend)
 
 
+# ---- key generation: one builder per option of each of the four key axes -------------------------------------------------
+class _KeySpec(object):
+    """Everything the per-axis key builders need for one activation shape: sizes, the block geometry after snapping the
+    block size (keynet/system.py:336-343) and the numeric options."""
+
+    def __init__(self, shape, blocksize, tileshape, strict, alpha, beta, gamma, hierarchical_blockshape, hierarchical_permute_at_level, seed):
+        (self.channels, self.height, self.width) = [int(v) for v in shape]
+        self.shape = (self.channels, self.height, self.width)
+        self.N = self.channels * self.height * self.width
+        (self.alpha, self.beta, self.gamma, self.seed, self.tileshape) = (alpha, beta, gamma, seed, tileshape)
+        (self.hblockshape, self.hlevels) = (hierarchical_blockshape, hierarchical_permute_at_level)
+        (self.blocksize, self.plane, self.blocknumel) = (blocksize, None, None)       # plane = size of the matrix one block key is tiled over
+        if blocksize is not None:
+            assert tileshape is None or (blocksize == tileshape[0] and blocksize == tileshape[1]), 'blocksize must equal the tile size'
+            if self.height == 1 and self.width == 1:
+                (self.blocksize, self.plane, self.blocknumel) = (self.N, self.N, self.N)              # a vector is one block
+            else:
+                if not strict and (self.height % blocksize != 0 or self.width % blocksize != 0):
+                    assert self.height == self.width, "Image must be square to correct ragged blocksize"
+                    self.blocksize = _util.find_closest_positive_divisor(self.height, blocksize)
+                (self.plane, self.blocknumel) = (self.height * self.width, self.blocksize * self.blocksize)
+
+    def need(self, **what):
+        for (name, ok) in what.items():
+            assert ok, 'this key needs a valid "%s"' % name
+
+    def tile_over_image(self, B):
+        """Block key B repeated over the spatial plane, then over the channels."""
+        return sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(B, (self.plane, self.plane)), (self.N, self.N))
+
+    def tiled_bias(self, b):
+        """Per-block bias vector repeated to the full length N (column vector)."""
+        return np.tile(b, int(np.ceil(self.N / self.blocknumel)))[0:self.N].reshape(self.N, 1)
+
+
+def _identity_pair(k):
+    return (sparse_identity_matrix(k.N), sparse_identity_matrix(k.N))
+
+
+def _global_permutation(k):
+    assert k.tileshape is None, "Global permutation is not tile compressible"
+    return sparse_permutation_matrix(k.N, withinverse=True)
+
+
+def _hierarchical(twist):
+    def build(k, c=None, cinv=None):
+        k.need(hierarchical_blockshape=k.hblockshape is not None, hierarchical_permute_at_level=k.hlevels is not None)
+        levels = _tolist(k.hlevels)
+        if max(k.height, k.width) / np.power(2, max(levels)) < 8 or (k.height == 1 and k.width == 1):
+            levels = []                                                     # too small to permute at these levels (system.py:365-366)
+        (Q, Qinv) = sparse_channelorder_to_pixelorder_matrix(k.shape, withinverse=True)
+        (G, Ginv) = hierarchical_block_permutation_matrix((k.height, k.width, k.channels), k.hblockshape, levels, min_blocksize=8, seed=k.seed,
+                                                          twist=twist, withinverse=True, strict=False)
+        (G, Ginv) = (Qinv.dot(G).dot(Q), Qinv.dot(Ginv).dot(Q))             # CxHxW -> HxWxC -> permute -> CxHxW
+        if c is not None:
+            (G, Ginv) = (c.dot(G).dot(cinv), c.dot(Ginv).dot(cinv))         # block memory order
+        return (G, Ginv)
+    build.wants_memoryorder = True
+    return build
+
+
+def _global_givens(k):
+    k.need(alpha=k.alpha is not None)
+    assert k.tileshape is None, "Global givens rotation orthogonal matrix is not tile compressible"
+    return sparse_orthogonal_matrix(k.N, int(k.alpha), balanced=True, withinverse=True)
+
+
+def _local_permutation(k):
+    k.need(blocksize=k.blocksize is not None and k.height == k.width)
+    g = k.tile_over_image(sparse_permutation_matrix(k.blocknumel))
+    return (g, g.transpose())
+
+
+def _local_doubly_stochastic(k):
+    k.need(blocksize=k.blocksize is not None and k.height == k.width, alpha=k.alpha is not None)
+    assert k.blocksize < 8192, "Blocksize %d must be less than 8192, since doubly_stochastic requires the direct inverse of a dense matrix" % k.blocksize
+    (g, ginv) = sparse_random_diagonally_dominant_doubly_stochastic_matrix(k.blocknumel, int(k.alpha), withinverse=True)
+    # the reference carries these blocks (and every matrix compiled with them) in float64; this path is fp32 throughout
+    return (k.tile_over_image(g.astype(np.float32)), k.tile_over_image(ginv.astype(np.float32)))
+
+
+def _local_givens(k):
+    k.need(blocksize=k.blocksize is not None and k.height == k.width, alpha=k.alpha is not None)
+    (g, ginv) = sparse_orthogonal_matrix(k.blocknumel, int(k.alpha), balanced=True, withinverse=True)
+    (Pb, Pbinv) = sparse_permutation_matrix(k.blocknumel, withinverse=True)
+    return (k.tile_over_image(Pb.dot(g)), k.tile_over_image(ginv.dot(Pbinv)))
+
+
+# photometric builders return HOMOGENEOUS pairs (the bias column lives in the last column)
+def _homogeneous(pair):
+    return (sparse_affine_to_linear(pair[0]), sparse_affine_to_linear(pair[1]))
+
+
+def _photo_identity(k):
+    return _homogeneous(_identity_pair(k))
+
+
+def _global_gain(k):
+    assert k.tileshape is None, "Global permutation is not tile compressible"
+    k.need(beta=k.beta is not None and k.beta > 0)
+    return _homogeneous(sparse_uniform_random_diagonal_matrix(k.N, k.beta, bias=1, withinverse=True))
+
+
+def _global_bias(draw):
+    def build(k):
+        k.need(gamma=k.gamma is not None and k.gamma > 0)
+        return diagonal_affine_to_linear(sparse_identity_matrix(k.N), draw(k), withinverse=True)
+    return build
+
+
+def _global_affine(k):
+    assert k.tileshape is None, "Global permutation is not tile compressible"
+    k.need(beta=k.beta is not None and k.beta > 0, gamma=k.gamma is not None and k.gamma > 0)
+    D = sparse_uniform_random_diagonal_matrix(k.N, k.beta, bias=1)
+    return diagonal_affine_to_linear(D, k.gamma * np.random.rand(k.N, 1), withinverse=True)
+
+
+def _blockwise_constant_bias(k):
+    k.need(blocksize=k.blocksize is not None)
+    per_block = k.gamma * np.random.rand(int(np.ceil(k.N // k.blocksize)), 1)          # one draw per block, spread over the block
+    return per_block.dot(np.ones((1, k.blocknumel))).flatten()[0:k.N].reshape(k.N, 1)
+
+
+def _local_gain(k):
+    k.need(blocksize=k.blocksize is not None, beta=k.beta is not None and k.beta > 0)
+    (d, dinv) = sparse_uniform_random_diagonal_matrix(k.blocknumel, k.beta, bias=1, withinverse=True)
+    return _homogeneous((_repeat_diagonal(d, k.N), _repeat_diagonal(dinv, k.N)))
+
+
+def _local_bias(k):
+    k.need(blocksize=k.blocksize is not None, gamma=k.gamma is not None and k.gamma > 0)
+    return diagonal_affine_to_linear(sparse_identity_matrix(k.N), bias=k.tiled_bias(k.gamma * np.random.rand(k.blocknumel)), withinverse=True)
+
+
+def _local_affine(k):
+    k.need(blocksize=k.blocksize is not None, beta=k.beta is not None and k.beta > 0, gamma=k.gamma is not None and k.gamma > 0)
+    d = sparse_uniform_random_diagonal_matrix(k.blocknumel, k.beta, bias=1)
+    return diagonal_affine_to_linear(_repeat_diagonal(d, k.N), bias=k.tiled_bias(k.gamma * np.random.rand(k.blocknumel)), withinverse=True)
+
+
+def _testing_only(k):
+    raise ValueError('blockwise_constant_bias supported for global_photometric testing only')
+
+
+_KEY_AXES = OrderedDict([      # in the order the reference draws from the RNG (keynet/system.py:357-464)
+    ('global geometric', {'identity': _identity_pair, 'permutation': _global_permutation, 'hierarchical_permutation': _hierarchical(False),
+                          'hierarchical_rotation': _hierarchical(True), 'givens_orthogonal': _global_givens}),
+    ('local geometric', {'identity': _identity_pair, 'permutation': _local_permutation, 'doubly_stochastic': _local_doubly_stochastic, 'givens_orthogonal': _local_givens}),
+    ('global photometric', {'identity': _photo_identity, 'uniform_random_gain': _global_gain, 'uniform_random_affine': _global_affine,
+                            'uniform_random_bias': _global_bias(lambda k: k.gamma * np.random.rand(k.N, 1)),
+                            'linear_bias': _global_bias(lambda k: (k.gamma / float(k.N)) * np.array(range(0, k.N)).reshape(k.N, 1)),
+                            'blockwise_constant_bias': _global_bias(_blockwise_constant_bias)}),
+    ('local photometric', {'identity': _photo_identity, 'uniform_random_gain': _local_gain, 'uniform_random_affine': _local_affine, 'uniform_random_bias': _local_bias,
+                           'blockwise_constant_bias': _testing_only}),
+])
+
+
 def keygen(shape, global_geometric, local_geometric, global_photometric, local_photometric, memoryorder='channel', alpha=None, beta=None, gamma=None, seed=None,
            hierarchical_blockshape=None, hierarchical_permute_at_level=None, blocksize=None, tileshape=None, strict=False):
-    """Compose A = C^-1 . p . g . P . G . C and its inverse for one activation shape (keynet/system.py:317-469).
+    """(A, A^-1) for one activation shape: A = C^-1 . p . g . P . G . C with C the memory order, G / g the global / local
+    geometric keys and P / p the global / local photometric keys (keynet/system.py:317-469).
 
-    RNG draws happen in the reference's order: global geometric, local geometric, global photometric, local
-    photometric.  All photometric options are supported (gain keys are monomial; bias / affine keys are monomial
-    plus a bias column, a family closed under products).  Givens-orthogonal and doubly-stochastic geometric keys are general
-    sparse keys (sparse.SparseKey): composed on the host like the reference's, compiled into the layers by the GPU SpGEMM."""
-    allowable_memoryorder = set(['channel', 'block'])
-    allowable_global_geometric = set(['identity', 'permutation', 'hierarchical_permutation', 'hierarchical_rotation', 'givens_orthogonal'])
-    allowable_local_geometric = set(['identity', 'permutation', 'doubly_stochastic', 'givens_orthogonal'])
-    allowable_photometric = set(['identity', 'uniform_random_gain', 'uniform_random_affine', 'uniform_random_bias', 'constant_bias', 'linear_bias', 'blockwise_constant_bias'])
-
-    (channels, height, width) = shape
-    N = int(np.prod(shape))
+    Each axis is one table lookup (_KEY_AXES); the builders draw from numpy's global RNG in the reference's order (global
+    geometric, local geometric, global photometric, local photometric).  Permutation / gain keys are MonomialKeys, bias /
+    affine keys MonomialKeys with a bias column (a family closed under products), Givens-orthogonal and doubly-stochastic
+    keys general SparseKeys composed on the host and compiled into the layers by the GPU SpGEMM."""
     if seed is not None:
         np.random.seed(seed)
-
-    (H, blocknumel) = (None, None)
-    if blocksize is not None:
-        if tileshape is not None:
-            assert blocksize == tileshape[0] and blocksize == tileshape[1]
-        if height == 1 and width == 1:
-            (blocksize, H, blocknumel) = (N, N, N)
-        elif not strict and (height % blocksize != 0 or width % blocksize != 0):
-            assert height == width, "Image must be square to correct ragged blocksize"
-            blocksize = _util.find_closest_positive_divisor(height, blocksize)
-            (H, blocknumel) = (height * width, blocksize * blocksize)
-        else:
-            (H, blocknumel) = (height * width, blocksize * blocksize)
-
+    k = _KeySpec(shape, blocksize, tileshape, strict, alpha, beta, gamma, hierarchical_blockshape, hierarchical_permute_at_level, seed)
     if memoryorder == 'channel':
-        (c, cinv) = (sparse_identity_matrix(N), sparse_identity_matrix(N))
+        (c, cinv) = (None, None)
+        (C, Cinv) = _photo_identity(k)
     elif memoryorder == 'block':
-        assert blocksize is not None
-        (c, cinv) = sparse_channelorder_to_blockorder_matrix(shape, blocksize, withinverse=True)
+        assert k.blocksize is not None, 'block memory order needs a blocksize'
+        (c, cinv) = sparse_channelorder_to_blockorder_matrix(k.shape, k.blocksize, withinverse=True)
+        (C, Cinv) = _homogeneous((c, cinv))
     else:
-        raise ValueError("Invalid memory order '%s' - must be in '%s'" % (memoryorder, str(allowable_memoryorder)))
-    (C, Cinv) = (sparse_affine_to_linear(c), sparse_affine_to_linear(cinv))
-
-    if global_geometric == 'identity':
-        (G, Ginv) = (sparse_identity_matrix(N), sparse_identity_matrix(N))
-    elif global_geometric == 'permutation':
-        assert tileshape is None, "Global permutation is not tile compressible"
-        (G, Ginv) = sparse_permutation_matrix(N, withinverse=True)
-    elif global_geometric in ('hierarchical_permutation', 'hierarchical_rotation'):
-        assert hierarchical_blockshape is not None and hierarchical_permute_at_level is not None
-        levels = _tolist(hierarchical_permute_at_level)
-        levels = levels if max(height, width) / np.power(2, max(levels)) >= 8 else []
-        levels = [] if (height == 1 and width == 1) else levels
-        (Q, Qinv) = sparse_channelorder_to_pixelorder_matrix((channels, height, width), withinverse=True)
-        (G, Ginv) = hierarchical_block_permutation_matrix((height, width, channels), hierarchical_blockshape, levels, min_blocksize=8, seed=seed,
-                                                          twist=(global_geometric == 'hierarchical_rotation'), withinverse=True, strict=False)
-        (G, Ginv) = (Qinv.dot(G).dot(Q), Qinv.dot(Ginv).dot(Q))     # CxHxW -> HxWxC -> permute -> CxHxW
-        if memoryorder != 'channel':
-            (G, Ginv) = (c.dot(G).dot(cinv), c.dot(Ginv).dot(cinv))
-    elif global_geometric == 'givens_orthogonal':
-        assert alpha is not None
-        assert tileshape is None, "Global givens rotation orthogonal matrix is not tile compressible"
-        (G, Ginv) = sparse_orthogonal_matrix(N, int(alpha), balanced=True, withinverse=True)
-    else:
-        raise ValueError("Invalid global geometric transform '%s' - must be in '%s'" % (global_geometric, str(allowable_global_geometric)))
-    (G, Ginv) = (sparse_affine_to_linear(G), sparse_affine_to_linear(Ginv))
-
-    if local_geometric == 'identity':
-        (g, ginv) = (sparse_identity_matrix(N), sparse_identity_matrix(N))
-    elif local_geometric == 'permutation':
-        assert blocksize is not None and height == width
-        g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(sparse_permutation_matrix(blocknumel), (H, H)), (N, N))   # spatial, then channel repeat
-        ginv = g.transpose()
-    elif local_geometric == 'doubly_stochastic':
-        assert blocksize is not None and alpha is not None and height == width
-        assert blocksize < 8192, "Blocksize %d must be less than 8192, since doubly_stochastic requires the direct inverse of a dense matrix" % blocksize
-        (g, ginv) = sparse_random_diagonally_dominant_doubly_stochastic_matrix(blocknumel, int(alpha), withinverse=True)
-        # the reference carries these blocks (and every matrix compiled with them) in float64; this path is fp32 throughout
-        g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(g.astype(np.float32), (H, H)), (N, N))        # spatial, then channel repeat
-        ginv = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(ginv.astype(np.float32), (H, H)), (N, N))
-    elif local_geometric == 'givens_orthogonal':
-        assert alpha is not None and blocksize is not None and height == width
-        (g, ginv) = sparse_orthogonal_matrix(blocknumel, int(alpha), balanced=True, withinverse=True)
-        (Pb, Pbinv) = sparse_permutation_matrix(blocknumel, withinverse=True)
-        (g, ginv) = (Pb.dot(g), ginv.dot(Pbinv))
-        g = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(g, (H, H)), (N, N))                             # spatial, then channel repeat
-        ginv = sparse_block_diagonal_repeat(sparse_block_diagonal_repeat(ginv, (H, H)), (N, N))
-    else:
-        raise ValueError("Invalid local geometric transform '%s' - must be in '%s'" % (local_geometric, str(allowable_local_geometric)))
-    (g, ginv) = (sparse_affine_to_linear(g), sparse_affine_to_linear(ginv))
-
-    if global_photometric == 'identity':
-        (P, Pinv) = (sparse_affine_to_linear(sparse_identity_matrix(N)), sparse_affine_to_linear(sparse_identity_matrix(N)))
-    elif global_photometric == 'uniform_random_gain':
-        assert tileshape is None, "Global permutation is not tile compressible"
-        assert beta is not None and beta > 0
-        (P, Pinv) = sparse_uniform_random_diagonal_matrix(N, beta, bias=1, withinverse=True)
-        (P, Pinv) = (sparse_affine_to_linear(P), sparse_affine_to_linear(Pinv))
-    elif global_photometric == 'uniform_random_bias':
-        assert gamma is not None and gamma > 0
-        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), gamma * np.random.rand(N, 1), withinverse=True)
-    elif global_photometric == 'linear_bias':
-        assert gamma is not None and gamma > 0
-        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), (gamma / float(N)) * np.array(range(0, N)).reshape(N, 1), withinverse=True)
-    elif global_photometric == 'uniform_random_affine':
-        assert tileshape is None, "Global permutation is not tile compressible"
-        assert beta is not None and beta > 0 and gamma is not None and gamma > 0
-        P = sparse_uniform_random_diagonal_matrix(N, beta, bias=1)
-        (P, Pinv) = diagonal_affine_to_linear(P, gamma * np.random.rand(N, 1), withinverse=True)
-    elif global_photometric == 'blockwise_constant_bias':
-        assert gamma is not None and gamma > 0
-        assert blocksize is not None
-        bias = gamma * np.random.rand(int(np.ceil(N // blocksize)), 1).dot(np.ones((1, blocknumel))).flatten()[0:N].reshape(N, 1)
-        (P, Pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), bias, withinverse=True)
-    else:
-        raise ValueError("Invalid global photometric transform '%s' - must be in '%s'" % (global_photometric, str(allowable_photometric)))
-
-    if local_photometric == 'identity':
-        (p, pinv) = (sparse_affine_to_linear(sparse_identity_matrix(N)), sparse_affine_to_linear(sparse_identity_matrix(N)))
-    elif local_photometric == 'uniform_random_gain':
-        assert blocksize is not None
-        assert beta is not None and beta > 0
-        (p, pinv) = sparse_uniform_random_diagonal_matrix(blocknumel, beta, bias=1, withinverse=True)
-        (p, pinv) = (_repeat_diagonal(p, N), _repeat_diagonal(pinv, N))
-        (p, pinv) = (sparse_affine_to_linear(p), sparse_affine_to_linear(pinv))
-    elif local_photometric == 'uniform_random_bias':
-        assert blocksize is not None
-        assert gamma is not None and gamma > 0
-        bias = np.tile(gamma * np.random.rand(blocknumel), int(np.ceil(N / blocknumel)))[0:N].reshape(N, 1)
-        (p, pinv) = diagonal_affine_to_linear(sparse_identity_matrix(N), bias=bias, withinverse=True)
-    elif local_photometric == 'uniform_random_affine':
-        assert blocksize is not None
-        assert beta is not None and beta > 0 and gamma is not None and gamma > 0
-        p = sparse_uniform_random_diagonal_matrix(blocknumel, beta, bias=1)
-        bias = np.tile(gamma * np.random.rand(blocknumel), int(np.ceil(N / blocknumel)))[0:N].reshape(N, 1)
-        (p, pinv) = diagonal_affine_to_linear(_repeat_diagonal(p, N), bias=bias, withinverse=True)
-    elif local_photometric == 'blockwise_constant_bias':
-        raise ValueError('blockwise_constant_bias supported for global_photometric testing only')
-    else:
-        raise ValueError("Invalid local photometric transform '%s' - must be in '%s'" % (local_photometric, str(allowable_photometric)))
-
-    A = Cinv.dot(p.dot(g.dot(P.dot(G.dot(C)))))
-    Ainv = Cinv.dot(Ginv.dot(Pinv.dot(ginv.dot(pinv.dot(C)))))
+        raise ValueError("Invalid memory order '%s' - must be in '%s'" % (memoryorder, str(['channel', 'block'])))
+    pairs = []
+    for ((axis, table), choice) in zip(_KEY_AXES.items(), (global_geometric, local_geometric, global_photometric, local_photometric)):
+        if choice not in table:
+            raise ValueError("Invalid %s transform '%s' - must be in '%s'" % (axis, choice, str(sorted(table))))
+        build = table[choice]
+        pair = build(k, c, cinv) if getattr(build, 'wants_memoryorder', False) else build(k)
+        pairs.append(_homogeneous(pair) if 'geometric' in axis else pair)
+    ((G, Ginv), (g, ginv), (P, Pinv), (p, pinv)) = pairs
+    # right-to-left products, in the reference's association (system.py:467-468): the fp32 roundings of gain keys depend on it
+    A = C
+    for K in (G, P, g, p, Cinv):
+        A = K.dot(A)
+    Ainv = C
+    for K in (pinv, ginv, Pinv, Ginv, Cinv):
+        Ainv = K.dot(Ainv)
     return (A, Ainv)
 
 

@@ -558,11 +558,16 @@ def test_save_and_load_compiled_keynet(tmp_path):
     for ((_, a), (_, b)) in zip(knet.keyedlayers(), k2.keyedlayers()):
         _assert_bit_exact(b.W, a.W.shape, *a.W.csr_arrays())
     y2 = k2.forward(s2.fromtensor(x).encrypt().astensor()).reshape(40, -1).numpy()
-    assert np.array_equal(y, y2)
+    # the loaded network rebuilds its pattern groups from the CSR (columns ascending) while the compiled one lists a group's
+    # columns in Toeplitz tap order: same matrices, different fp32 summation order at batch >= 32 ...
+    assert np.allclose(y, y2, rtol=1e-5, atol=1e-6 * np.abs(y).max())
+    # ... and bit-identical results on the CSR kernel (small batch)
+    y8 = knet.forward(sensor.fromtensor(x[:8]).encrypt().astensor()).reshape(8, -1).numpy()
+    assert np.array_equal(y8, k2.forward(s2.fromtensor(x[:8]).encrypt().astensor()).reshape(8, -1).numpy())
     # public release: keys removed, the keyed network still runs on ciphertext
     xc = sensor.fromtensor(x).encrypt().astensor()
     (s3, k3) = io.load(io.save(str(tmp_path / 'public.keynet'), None, knet.public()))
-    assert s3 is None and np.array_equal(k3.forward(xc).reshape(40, -1).numpy(), y)
+    assert s3 is None and np.allclose(k3.forward(xc).reshape(40, -1).numpy(), y, rtol=1e-5, atol=1e-6 * np.abs(y).max())
 
 
 # ---------------------------------------------------------------------------------------------
