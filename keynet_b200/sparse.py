@@ -1543,7 +1543,25 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
         wn = W.cpu().numpy()
         bn = None if bias is None else torch.as_tensor(bias).detach().cpu().numpy().astype(np.float32)
         fits = n_in + 1 <= 8192                      # taps per pixel the fused CSR writer sorts in shared memory
-        M_ = _keyed_conv_direct((int(n_in), 1, 1, int(n_out), 1, 1, 1, bn is not None), wn, bn, A, Ainv, rows, col_remap, n_cols_phys, want_csr and fits, build_groups, dev)
+        (A_, rows_, n_out_) = (A, rows, int(n_out))
+        if rows is not None:
+            # a row shard of a linear layer is a smaller linear layer: its weight rows in the shard's own order, the output
+            # key reduced to the gains of those rows (one group must hold EVERY row it is given -- residual dense rows on
+            # the CSR kernel cost a warp 25 k sequential taps each)
+            sel_ = np.arange(int(rows[0]), int(rows[1]), dtype=np.int64) if isinstance(rows, tuple) else np.ascontiguousarray(rows, dtype=np.int64)
+            src_ = sel_ if A is None else A.perm[sel_]
+            main_ = src_ < n_out
+            n_out_ = int(main_.sum())
+            wn = np.ascontiguousarray(wn[src_[main_]])
+            bn = None if bn is None else np.ascontiguousarray(bn[src_[main_]])
+            rows_ = np.where(main_, np.cumsum(main_) - 1, n_out_).astype(np.int64)          # local row -> row of the reduced layer
+            scale_ = np.ones(n_out_ + 1, dtype=np.float32)
+            if A is not None:
+                scale_[rows_] = A.scale[sel_]
+            A_ = MonomialKey(np.arange(n_out_ + 1), scale_)
+        M_ = None
+        if n_out_ > 0:
+            M_ = _keyed_conv_direct((int(n_in), 1, 1, n_out_, 1, 1, 1, bn is not None), wn, bn, A_, Ainv, rows_, col_remap, n_cols_phys, want_csr and fits, build_groups, dev)
         if M_ is not None and (fits or not want_csr):
             return M_
         pg = M_._pg if M_ is not None else None      # groups built directly, canonical CSR through the two-kernel path below

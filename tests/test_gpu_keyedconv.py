@@ -146,3 +146,36 @@ def test_fused_conv_equals_oracle_compile():
     got = sparse.keyed_toeplitz_conv2d((C, U, V), f, b, 1, A, Ainv)
     o = ko.sort_indices(ko.key_compile(ko.monomial_key(A.perm, A.scale), ko.toeplitz_conv2d((C, U, V), f, b, 1), ko.monomial_key(Ainv.perm, Ainv.scale)))
     _same(got.csr_arrays(), (o.indptr, o.indices, o.data), 'oracle')
+
+
+@pytest.mark.parametrize('with_last', [False, True])
+def test_fused_linear_row_shard_is_one_group(with_last):
+    """A row shard of a linear layer (dist.py) keeps every row in ONE pattern group even when a weight is exactly zero
+    (a residual dense row on the CSR kernel costs milliseconds at VGG16 fc6 size)."""
+    from keynet_b200 import sparse
+    rs = np.random.RandomState(8)
+    (n_out, n_in) = (200, 5000)
+    w = rs.randn(n_out, n_in).astype(np.float32); w[3, 7] = 0; w[150, 4999] = 0
+    b = rs.randn(n_out).astype(np.float32)
+    (A, Ainv) = _keys(rs, n_out + 1, n_in + 1, True, True, True)
+    rows = rs.permutation(n_out)[:77].astype(np.int64)
+    if with_last:
+        rows = np.concatenate([rows[:30], [n_out], rows[30:]])
+    n_phys = n_in + 1 + 5
+    remap = np.concatenate([rs.permutation(n_phys - 1)[:n_in], [n_phys - 1]]).astype(np.int64)
+    got = sparse.keyed_linear(torch.from_numpy(w), torch.from_numpy(b), A, Ainv, rows=rows, col_remap=remap, n_cols_phys=n_phys)
+    try:
+        sparse.direct_compile_enabled(False)
+        ref = sparse.keyed_linear(torch.from_numpy(w), torch.from_numpy(b), A, Ainv, rows=rows, col_remap=remap, n_cols_phys=n_phys)
+    finally:
+        sparse.direct_compile_enabled(True)
+    _same(got.csr_arrays(), ref.csr_arrays(), 'sharded linear CSR')
+    assert got._pg is not None and len(got._pg.classes) == 1 and got._pg.classes[0]['G'] == 77
+    assert (got._pg.rest is None) == (not with_last)
+    _same(_groups_to_csr(got), ref.csr_arrays(), 'sharded linear groups')
+    only = sparse.keyed_linear(torch.from_numpy(w), torch.from_numpy(b), A, Ainv, rows=rows, col_remap=remap, n_cols_phys=n_phys, want_csr=False)
+    assert only._data is None and only.nnz() == ref.nnz()
+    X = torch.randn(n_phys, 64, device='cuda')
+    y = sparse.spmm(only, X)
+    y_ref = sparse.spmm(sparse.SparseMatrix((ref.shape, *ref.csr_arrays())), X)
+    assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5 * float(y_ref.abs().max()))
