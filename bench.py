@@ -792,7 +792,7 @@ def bench_keycompile(args, rank, local_rank):
         b = bands[state['i']]; state['i'] += 1
         torch.cuda.synchronize()
         best = None
-        for rep in range(2):                                            # second pass: allocator warm
+        for rep in range(2):                                            # second pass: the caching allocator holds the blocks of the first
             torch.cuda.synchronize()
             (e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             e0.record()
@@ -803,7 +803,6 @@ def bench_keycompile(args, rank, local_rank):
             best = ms if best is None else min(best, ms)
             if rep == 0:
                 del L
-                torch.cuda.empty_cache()
         W = L.W
         nnz = W.nnz()
         # bit-exact check of the band rows: canonical (sorted) oracle rows against the GPU rows
@@ -813,14 +812,15 @@ def bench_keycompile(args, rank, local_rank):
         ref = ko.sort_indices(b['W'])
         ok = bool(torch.equal((end - beg).cpu(), torch.from_numpy(np.diff(ref.indptr))))
         if ok:
-            take = torch.cat([torch.arange(int(s), int(e), device='cuda') for (s, e) in zip(beg.tolist(), end.tolist())]) if len(r) else torch.zeros(0, dtype=torch.int64, device='cuda')
+            lens = (end - beg)
+            take = torch.repeat_interleave(beg, lens) + (torch.arange(int(lens.sum()), device='cuda') - torch.repeat_interleave(torch.cumsum(lens, 0) - lens, lens))
             ok = bool(np.array_equal(W._indices[take].cpu().numpy(), ref.indices)) and bool(np.array_equal(W._data[take].cpu().numpy().view(np.uint32), ref.data.view(np.uint32)))
-        h = hashlib.sha256()
-        for t in (W._indptr, W._indices, W._data):
-            h.update(t.cpu().numpy().tobytes())
+        # digest of the whole layer computed on the device (120 GB of CSR do not go through the host): wrapping 64-bit sums of
+        # the row pointers, the column indices and the value bit patterns
+        digest = '%016x' % ((int(W._indptr.sum().item()) * 1000003 + int(W._indices.sum(dtype=torch.int64).item()) * 10007 + int(W._data.view(torch.int32).sum(dtype=torch.int64).item())) & 0xffffffffffffffff)
         bytes_alg = nnz * 8 + (W.shape[0] + 1) * 8 + (W.shape[0] + W.shape[1]) * 4      # write W_hat once (+ the key vectors); the Toeplitz source is generated, not read
         rows.append({'layer': L._repr, 'shape': list(W.shape), 'nnz': int(nnz), 'gpu_ms': round(best, 3), 'csr_bytes': int(bytes_alg), 'gbs': bytes_alg / (best * 1e-3) / 1e9,
-                     'hbm_frac': bytes_alg / (best * 1e-3) / 1e9 / peak, 'band_rows': int(len(b['rows'])), 'band_bit_exact': ok, 'sha256': h.hexdigest()[:16]})
+                     'hbm_frac': bytes_alg / (best * 1e-3) / 1e9 / peak, 'band_rows': int(len(b['rows'])), 'band_bit_exact': ok, 'digest': digest})
         del W
         L.W = None
         torch.cuda.empty_cache()

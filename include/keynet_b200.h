@@ -234,6 +234,24 @@ int kn_conv2d_groups_index(const kn_conv2d_desc *desc, const int32_t *pix, int64
 int kn_conv2d_groups_values(const kn_conv2d_desc *desc, const float *weight, const float *bias, const int32_t *block_pix, int64_t n_blocks,
                             const int32_t *row_of_src, const float *row_scale, const float *col_scale, int32_t K_pad, float *vals, void *stream);
 
+/* ---- spatially tiled tensor-core product for keyed conv layers with G <= 128 output channels (csrc/pgtile_tc.cu) -----
+ * Same product as kn_spmm_pg_tc_f32 (SparseMatrix.torchdot, keynet/sparse.py:488-492, of a Toeplitz conv layer of
+ * keynet/sparse.py:163-203 under permutation-only keys), organised by TILES of th x tw neighbouring output pixels: the
+ * union of a tile's input positions is gathered once per 16-channel chunk and the P*Q weight slabs of the chunk are
+ * loaded once and shared by all pixels of the tile -- those layers are bound by L2 -> SM traffic, not by the tensor pipe.
+ *   kn_conv2d_tiles_index  tile tables: tile_cols[tile][(th-1)*stride+P][(tw-1)*stride+Q][C] activation row of every
+ *                          (input position, channel) under the input key (col_map), -1 outside the image;
+ *                          tile_rows[tile][th*tw][M] output row of every (pixel, channel).  tile_origin[tile] = top-left
+ *                          output pixel (ku*Vo + kv) of the tile.
+ *   kn_spmm_tile_tc_f32    maps_host: TMA descriptors (kn_pg_tc_tensormaps) of the TAP-major weight matrix Wt[G][K_pad],
+ *                          k = tap*C + c, bias at k = P*Q*C, zero padded to a multiple of 16; bias_col = activation row
+ *                          of the homogeneous coordinate.  C % 16 == 0, th*tw <= 6, union positions <= 32. */
+int kn_conv2d_tiles_index(const kn_conv2d_desc *desc, const int32_t *tile_origin, int64_t n_tiles, int32_t th, int32_t tw,
+                          const int32_t *row_of_src, const int32_t *col_map, int32_t *tile_cols, int32_t *tile_rows, void *stream);
+int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, const int32_t *tile_rows, int32_t bias_col, int64_t n_tiles,
+                        int32_t C, int32_t G, int32_t th, int32_t tw, int32_t stride, int32_t P, int32_t Q,
+                        const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left
  * for explicit matrices, e.g. sensor keys / ReLU keys, keynet/layer.py:46). */
 int kn_csr_gather_rows_count(const int64_t *indptr, const int64_t *row_ids, int64_t n_rows, int64_t *row_nnz, void *stream);

@@ -139,16 +139,22 @@ __device__ __forceinline__ void bitonic_sort_kp(int32_t *keys, int32_t *pay, int
 }
 
 // ---- fill: one CTA per output pixel ------------------------------------------------------------------------------------
+// BIG = false: the pixel's (column, tap) list is built and sorted in shared memory (up to kSortCap taps).
+// BIG = true : a single pixel with more taps than that (a dense linear layer: 25 089 columns for VGG16 fc6): the list lives in a
+//              global scratch buffer, is sorted once by CTA 0 of a preceding launch (sort_only), and every CTA then streams a
+//              slice of the M rows from it.
+template <bool BIG>
 __global__ void __launch_bounds__(kThreads)
 keyed_conv_fill_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const float *__restrict__ bias,
                        const int32_t *__restrict__ pix, int64_t n_groups, const int32_t *__restrict__ row_of_src,
                        const int32_t *__restrict__ col_map, const float *__restrict__ row_scale, const float *__restrict__ col_scale,
-                       int keep_zeros, const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data)
+                       int keep_zeros, const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data,
+                       int32_t *scratch, int cap, int sort_only)
 {
     extern __shared__ int32_t smem[];
-    int32_t *s_key = smem;                       // new column of every tap (sorted ascending)
-    int32_t *s_tap = smem + kSortCap;            // weight offset of the tap inside a channel slab; -1 = bias entry
-    float *s_cs = reinterpret_cast<float *>(smem + 2 * kSortCap);       // column scale of the tap (only with col_scale)
+    int32_t *s_key = BIG ? scratch : smem;                   // new column of every tap (sorted ascending)
+    int32_t *s_tap = BIG ? scratch + cap : smem + kSortCap;  // weight offset of the tap inside a channel slab; -1 = bias entry
+    float *s_cs = reinterpret_cast<float *>(BIG ? scratch + 2 * cap : smem + 2 * kSortCap);       // column scale of the tap (only with col_scale)
     __shared__ int s_unsorted;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int UoVo = (d.U / d.stride) * (d.V / d.stride);
@@ -156,11 +162,12 @@ keyed_conv_fill_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const
     const int K_src = d.C * d.U * d.V;
     const int CPQ = d.C * d.P * d.Q;
 
-    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    for (int64_t g = BIG ? 0 : blockIdx.x; g < n_groups; g += BIG ? n_groups : gridDim.x) {
         const int px = pix ? pix[g] : (int)g;
         const PixGeom geo = pix_geom(d, px);
         const int K_main = d.C * geo.np * geo.nq;
         const int K = K_main + (d.has_bias ? 1 : 0);
+        if (!BIG || sort_only) {
         if (threadIdx.x == 0) s_unsorted = 0;
         __syncthreads();
         int unsorted = 0;
@@ -188,8 +195,10 @@ keyed_conv_fill_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const
             }
         }
         __syncthreads();
-        // stream the M rows of this pixel: one warp per row, 32 sorted taps per step
-        for (int m = warp; m < d.M; m += kWarps) {
+        }
+        if (BIG && sort_only) return;                           // (single pixel: every thread of the one CTA leaves together)
+        // stream the M rows of this pixel: one warp per row, 32 sorted taps per step (BIG: the rows are spread over the grid)
+        for (int m = BIG ? (int)blockIdx.x * kWarps + warp : warp; m < d.M; m += BIG ? (int)gridDim.x * kWarps : kWarps) {
             const int64_t s = (int64_t)m * UoVo + px;
             const int64_t r = row_of_src ? row_of_src[s] : s;
             if (r < 0) continue;
@@ -340,13 +349,28 @@ KN_API int kn_keyed_conv2d_fill(const kn_conv2d_desc *desc, const float *weight,
     KN_REQUIRE(weight && out_indptr && out_indices && out_data, "keyed_conv: null pointer");
     KN_REQUIRE(!desc->has_bias || bias, "keyed_conv: has_bias set but bias is null");
     const int64_t K_max = (int64_t)desc->C * desc->P * desc->Q + (desc->has_bias ? 1 : 0);
-    if (K_max > kSortCap) { kn_set_error("keyed_conv: %lld taps per output pixel exceed the shared-memory sort (%d): use the two-kernel path", (long long)K_max, kSortCap); return KN_ERR_UNSUPPORTED; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K_max > kSortCap) {
+        // more taps per pixel than the shared-memory sort holds: supported for ONE pixel (dense linear layers), whose list is
+        // sorted once in a stream-ordered scratch buffer and then shared by the whole grid
+        if (n_groups != 1 || K_max > (1 << 24)) { kn_set_error("keyed_conv: %lld taps per output pixel exceed the shared-memory sort (%d): use the two-kernel path", (long long)K_max, kSortCap); return KN_ERR_UNSUPPORTED; }
+        int32_t *scratch = nullptr;
+        KN_CUDA(cudaMallocAsync((void **)&scratch, (size_t)K_max * 12, s));
+        keyed_conv_fill_kernel<true><<<1, kThreads, 0, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
+                                                             out_indptr, out_indices, out_data, scratch, (int)K_max, 1);
+        keyed_conv_fill_kernel<true><<<grid_for(desc->M, kWarps, 8), kThreads, 0, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
+                                                                                        out_indptr, out_indices, out_data, scratch, (int)K_max, 0);
+        const cudaError_t e = cudaGetLastError();
+        KN_CUDA(cudaFreeAsync(scratch, s));
+        if (e != cudaSuccess) { kn_set_error("keyed_conv: launch failed: %s", cudaGetErrorString(e)); return KN_ERR_CUDA; }
+        return KN_OK;
+    }
     const size_t smem = (size_t)kSortCap * 4 * (col_scale ? 3 : 2);
     KN_ONCE_PER_DEVICE {
-        KN_CUDA(cudaFuncSetAttribute(keyed_conv_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4 * 3));
+        KN_CUDA(cudaFuncSetAttribute(keyed_conv_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4 * 3));
     }
-    keyed_conv_fill_kernel<<<grid_for(n_groups > 0 ? n_groups : 1, 1, 2), kThreads, smem, (cudaStream_t)stream>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
-                                                                                                     out_indptr, out_indices, out_data);
+    keyed_conv_fill_kernel<false><<<grid_for(n_groups > 0 ? n_groups : 1, 1, 2), kThreads, smem, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
+                                                                                                out_indptr, out_indices, out_data, nullptr, 0, 0);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }

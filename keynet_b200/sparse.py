@@ -828,6 +828,16 @@ def tensor_cores_enabled(flag=None):
 
 _CLUSTERS = [True]
 _DIRECT = [os.environ.get('KEYNET_B200_DIRECT_COMPILE', '1') != '0']
+_TILES = [os.environ.get('KEYNET_B200_TILES', '1') != '0']
+
+
+def tiles_enabled(flag=None):
+    """Switch for the spatially tiled tensor-core kernel of conv layers with G <= 128 (csrc/pgtile_tc.cu); off = one output
+    pixel per CTA (csrc/pgroup_tc.cu).  A/B measurements and tests."""
+    if flag is not None:
+        _TILES[0] = bool(flag)
+    return _TILES[0]
+
 
 
 def direct_compile_enabled(flag=None):
@@ -1113,6 +1123,10 @@ class PatternGroups(object):
                 if saved[0]:
                     _native.set_output_peers(*saved)
                 check(L.kn_splitk_reduce_f32(ptr(part), k['S'], k['G'], ptr(c['rows']), ptr(y), N, N, flags, stream_ptr()))
+            elif c.get('tile') is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled() and tiles_enabled():
+                t = c['tile']
+                check(L.kn_spmm_tile_tc_f32(t['maps'], ptr(t['cols']), ptr(t['rows']), t['bias_col'], t['n_tiles'], t['C'], t['G'], t['th'], t['tw'], t['stride'], t['P'], t['Q'],
+                                            ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
             elif c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
                 check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
                                           ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
@@ -1400,6 +1414,8 @@ def _keyed_conv_direct(geom, wq, bq, A, Ainv, rows, col_remap, n_cols_phys, want
     pg.shape = W.shape
     cls = dict(G=M, K_pad=K_pad, n_groups=ng, rows=rows_t, cols=cols, vals=vals, tc=None, group_k=group_k, block_of=block_of, n_blocks=n_blocks)
     PatternGroups._finish_class(cls, C * P * Q + (1 if has_bias else 0), cid, Kp)
+    if cls['tc'] is not None and not scaled and has_bias and UoVo > 1:
+        cls['tile'] = _conv_tiles(desc, (C, U, V, M, P, Q, int(stride)), wq, bq, pix_np, row_of_src, col_map, int(AinvP.perm[K_src - 1]), dev)
     pg.classes.append(cls)
     pg.grouped_rows = ng * M
     pg.padded_values = n_blocks * M * K_pad
@@ -1418,6 +1434,46 @@ def _keyed_conv_direct(geom, wq, bq, A, Ainv, rows, col_remap, n_cols_phys, want
     W._pg = pg
     return W
 
+
+
+def _conv_tiles(desc, geom, wq, bq, pix_np, row_of_src, col_map, bias_col, dev):
+    """Tile format of a conv layer for the spatially tiled tensor-core kernel (csrc/pgtile_tc.cu), or None when the layer
+    does not qualify: G <= 128 output channels (taller groups are tensor-bound on the per-pixel kernel already), C a
+    multiple of 16, the image divisible into th x tw tiles and the pixel set a union of whole tiles."""
+    (C, U, V, M, P, Q, stride) = geom
+    L = _native.lib()
+    Gp = (M + 15) // 16 * 16
+    if not (32 <= Gp <= 128 and C % 16 == 0 and C >= 16):
+        return None
+    (th, tw) = (2, 2) if Gp <= 96 else (1, 2)
+    (Uo, Vo) = (U // stride, V // stride)
+    (uh, uw) = ((th - 1) * stride + P, (tw - 1) * stride + Q)
+    if Uo % th != 0 or Vo % tw != 0 or uh * uw > 32 or th * tw * Gp + 4 * 32 > 512:
+        return None
+    slab = 2 * Gp * 64
+    if (226 * 1024 - (uh * uw * C * 4 + 4096)) // slab < P * Q + 1:
+        return None
+    (py, px) = (pix_np // Vo, pix_np % Vo)
+    origin = (py // th * th) * Vo + (px // tw * tw)
+    (tiles, counts) = np.unique(origin, return_counts=True)
+    if not np.all(counts == th * tw):
+        return None                                   # the shard cuts through a tile
+    n_tiles = len(tiles)
+    n_taps = P * Q
+    K_pad = n_taps * C + 16
+    Wt = np.zeros((M, K_pad), dtype=np.float32)
+    Wt[:, :n_taps * C] = np.ascontiguousarray(wq, dtype=np.float32).reshape(M, C, n_taps).transpose(0, 2, 1).reshape(M, n_taps * C)      # k = tap * C + c
+    Wt[:, n_taps * C] = bq
+    w = torch.from_numpy(Wt).to(dev).reshape(-1)
+    (hi, lo) = (torch.empty_like(w), torch.empty_like(w))
+    check(L.kn_pg_tc_split(ptr(w), w.numel(), ptr(hi), ptr(lo), stream_ptr()))
+    maps = ctypes.create_string_buffer(4 * 128)
+    check(L.kn_pg_tc_tensormaps(ptr(hi), ptr(lo), M, M, K_pad, maps))
+    t_origin = torch.from_numpy(tiles.astype(np.int32)).to(dev)
+    tile_cols = torch.empty(n_tiles * uh * uw * C, dtype=torch.int32, device=dev)
+    tile_rows = torch.empty(n_tiles * th * tw * M, dtype=torch.int32, device=dev)
+    check(L.kn_conv2d_tiles_index(desc, ptr(t_origin), n_tiles, th, tw, ptr(row_of_src), ptr(col_map), ptr(tile_cols), ptr(tile_rows), stream_ptr()))
+    return dict(maps=maps, hi=hi, lo=lo, cols=tile_cols, rows=tile_rows, bias_col=bias_col, n_tiles=n_tiles, C=C, G=M, th=th, tw=tw, stride=stride, P=P, Q=Q)
 
 
 def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True, col_remap=None, n_cols_phys=None, want_csr=True):
@@ -1542,7 +1598,6 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
         # a linear layer is a 1x1 convolution on a 1x1 image: one output "pixel", one pattern group holding every row
         wn = W.cpu().numpy()
         bn = None if bias is None else torch.as_tensor(bias).detach().cpu().numpy().astype(np.float32)
-        fits = n_in + 1 <= 8192                      # taps per pixel the fused CSR writer sorts in shared memory
         (A_, rows_, n_out_) = (A, rows, int(n_out))
         if rows is not None:
             # a row shard of a linear layer is a smaller linear layer: its weight rows in the shard's own order, the output
@@ -1561,10 +1616,10 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
             A_ = MonomialKey(np.arange(n_out_ + 1), scale_)
         M_ = None
         if n_out_ > 0:
-            M_ = _keyed_conv_direct((int(n_in), 1, 1, n_out_, 1, 1, 1, bn is not None), wn, bn, A_, Ainv, rows_, col_remap, n_cols_phys, want_csr and fits, build_groups, dev)
-        if M_ is not None and (fits or not want_csr):
+            M_ = _keyed_conv_direct((int(n_in), 1, 1, n_out_, 1, 1, 1, bn is not None), wn, bn, A_, Ainv, rows_, col_remap, n_cols_phys, want_csr, build_groups, dev)
+        if M_ is not None:
             return M_
-        pg = M_._pg if M_ is not None else None      # groups built directly, canonical CSR through the two-kernel path below
+        pg = None
     else:
         pg = None
     b = torch.as_tensor(bias).detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None

@@ -179,3 +179,22 @@ def test_fused_linear_row_shard_is_one_group(with_last):
     y = sparse.spmm(only, X)
     y_ref = sparse.spmm(sparse.SparseMatrix((ref.shape, *ref.csr_arrays())), X)
     assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5 * float(y_ref.abs().max()))
+
+
+def test_fused_linear_wide_rows_sorted_in_global_memory():
+    """More columns than the shared-memory sort holds (VGG16 fc6: 25 089): the single group's column list is sorted once in a
+    scratch buffer and shared by the whole grid."""
+    from keynet_b200 import sparse
+    rs = np.random.RandomState(9)
+    (n_out, n_in) = (70, 9001)
+    w = rs.randn(n_out, n_in).astype(np.float32); w[5, 100] = 0
+    b = rs.randn(n_out).astype(np.float32)
+    for gain in (False, True):
+        (A, Ainv) = _keys(rs, n_out + 1, n_in + 1, True, True, gain)
+        got = sparse.keyed_linear(torch.from_numpy(w), torch.from_numpy(b), A, Ainv)
+        try:
+            sparse.direct_compile_enabled(False)
+            ref = sparse.keyed_linear(torch.from_numpy(w), torch.from_numpy(b), A, Ainv)
+        finally:
+            sparse.direct_compile_enabled(True)
+        _same(got.csr_arrays(), ref.csr_arrays(), 'wide linear CSR')
