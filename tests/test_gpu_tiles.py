@@ -15,7 +15,7 @@ def _keys(rs, n_out, n_in, permute):
 
 
 CASES = [  # (C, U, M, k, stride)
-    (16, 8, 32, 3, 1), (32, 6, 64, 3, 1), (64, 4, 96, 3, 1), (128, 4, 128, 3, 1), (16, 8, 64, 3, 2), (48, 6, 80, 3, 1), (16, 6, 48, 1, 1)]
+    (16, 8, 32, 3, 1), (32, 6, 64, 3, 1), (64, 4, 96, 3, 1), (128, 4, 128, 3, 1), (16, 8, 64, 3, 2), (48, 6, 80, 3, 1)]
 
 
 @pytest.mark.parametrize('case', CASES)
