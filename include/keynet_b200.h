@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KN_ABI_VERSION 1
+#define KN_ABI_VERSION 2
 
 typedef enum {
     KN_OK = 0,
@@ -49,16 +49,20 @@ const char *kn_last_error(void);
 int kn_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *total_mem_bytes);
 
 /* ---- fused SpMM + all-gather (kernel K5) --------------------------------------------------------------
- * After kn_output_peers(ptrs, n) every kn_spmm_* call of the calling thread stores each output row to ALL n buffers
- * (ptrs[i] = address on peer i of the same Y argument; NVLink peer mappings, e.g. torch symmetric memory) instead of
- * to its Y argument: the row-sharded layer writes its slot of every rank's gathered activation buffer from the
- * epilogue, so no separate all-gather runs.  n = 0 restores single-destination stores.  HOST array of device pointers. */
-int kn_output_peers(const uint64_t *peer_y_host, int32_t n);
-/* Same, with a need mask: row_mask[r] (DEVICE memory, one byte per row of the Y argument) has bit i set when peer i
- * reads output row r in its next layer; only those copies are stored.  A conv layer sharded by pixels then sends its
- * halo rows to the neighbouring shard and nothing else -- the all-gather of keynet's row-sharded layers (BASELINE
- * north_star) degenerates to a halo exchange.  row_mask = NULL behaves like kn_output_peers. */
-int kn_output_peers_masked(const uint64_t *peer_y_host, int32_t n, const uint8_t *row_mask);
+ * Every kn_spmm_* entry point (and kn_splitk_reduce_f32) takes `const kn_peers *peers`.  NULL (or n = 0): each output row
+ * is stored to the Y argument.  Otherwise each output row is stored to ALL n buffers y[i] instead -- y[i] = device address
+ * on rank i of the same Y argument (NVLink peer mappings, e.g. torch symmetric memory; the own rank is one of them): a
+ * row-sharded layer writes its slot of every rank's gathered activation buffer from the epilogue, so no separate
+ * all-gather runs.  row_mask (optional, DEVICE memory, one byte per output row of Y): bit i set = rank i reads that row in
+ * its next layer; only those copies are stored, so a conv layer sharded by pixels sends its halo rows to the neighbouring
+ * shard and nothing else -- the all-gather of keynet's row-sharded layers (BASELINE north_star) degenerates to a halo
+ * exchange.  The argument is read during the call only: no state is kept between calls or threads. */
+typedef struct kn_peers {
+    int32_t n;                  /* destinations, 0..8 */
+    int32_t reserved;
+    uint64_t y[8];              /* device addresses */
+    const uint8_t *row_mask;    /* device memory or NULL */
+} kn_peers;
 
 /* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------
  * Replaces SparseMatrix.torchdot (keynet/sparse.py:488-492 -> scipy csr_matvecs), called from
@@ -67,14 +71,14 @@ int kn_output_peers_masked(const uint64_t *peer_y_host, int32_t n, const uint8_t
 int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *data,
                     int64_t n_rows, int64_t n_cols,
                     const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
-                    uint32_t flags, void *stream);
+                    uint32_t flags, const kn_peers *peers, void *stream);
 
 /* Same product for a subset of rows: output row i is written to Y[out_rows[i]] (out_rows NULL = identity).
  * Used for the rows of a layer matrix that are not covered by pattern groups (below). */
 int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const float *data,
                          int64_t n_rows, int64_t n_cols, const int32_t *out_rows,
                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
-                         uint32_t flags, void *stream);
+                         uint32_t flags, const kn_peers *peers, void *stream);
 
 /* ---- general key compile: C = A . B on CSR (csrc/spgemm.cu) ------------------------------------------------
  * Replaces the two scipy csr_matmat calls of `A.dot(W).dot(Ainv)` (keynet/layer.py:35,59,70) for keys with several
@@ -108,12 +112,12 @@ int kn_pg_verify(const int64_t *indptr, const int32_t *indices, const int64_t *r
 int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float *data, const int64_t *rows,
                int64_t n_groups, int32_t G, int32_t K_pad, int32_t *cols, float *vals, void *stream);
 int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
-                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
 /* Split-K epilogue for a layer that is ONE huge group (dense fully connected layers): the K range is cut into S slices
  * that run as S groups of kn_spmm_pg_tc_f32 / kn_spmm_pg_f32 writing partial rows part[s*G + i][n_vecs]; this adds them:
  * Y[rows[i]][:] = relu?(sum_s part[s*G + i][:]) (and performs the peer stores of the row-sharded path). */
-int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
 /* Clustered variant for short reductions (csrc/pgcluster.cu; G <= 256, walked 16 rows at a time above 16): the groups of a tile of neighbouring output pixels
  * form a cluster with ONE union column list that is staged in shared memory once per (cluster, 128 batch columns), so a
@@ -128,7 +132,7 @@ int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t 
 #define KN_CG_MAX_UNION 224
 int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t *ucols, const int32_t *rows, const int32_t *lidx, const float *valsT,
                    const int32_t *group_k, const int32_t *block_of, int64_t n_clusters, int32_t G, int32_t K_pad, int32_t u_max, int32_t g_max,
-                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+                   const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
 /* Tensor-core variant (csrc/pgroup_tc.cu): tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo),
  * fp32 accumulators in TMEM, weight blocks by TMA, gathered activations written into the UMMA layout by producer
@@ -140,7 +144,7 @@ int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
 int kn_pg_tc_split(const float *vals, int64_t n, float *vals_hi, float *vals_lo, void *stream);
 int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64_t n_rows_total, int32_t G, int32_t K_pad, void *maps_out_host);
 int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
-                      const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+                      const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
 /* debug aid: record clock64 phase stamps (entry, prologue, first stage, last MMA issue, accumulators ready, epilogue
  * stored, teardown) of CTA `cta` of the next kn_spmm_pg_tc_f32 launches (-1 = off); out_host (nullable) receives 8 values. */
@@ -250,7 +254,7 @@ int kn_conv2d_tiles_index(const kn_conv2d_desc *desc, const int32_t *tile_origin
                           const int32_t *row_of_src, const int32_t *col_map, int32_t *tile_cols, int32_t *tile_rows, void *stream);
 int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, const int32_t *tile_rows, int32_t bias_col, int64_t n_tiles,
                         int32_t C, int32_t G, int32_t th, int32_t tw, int32_t stride, int32_t P, int32_t Q,
-                        const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream);
+                        const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left
  * for explicit matrices, e.g. sensor keys / ReLU keys, keynet/layer.py:46). */

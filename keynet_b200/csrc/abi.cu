@@ -43,17 +43,18 @@ static thread_local KnPeers g_peers = {0, {nullptr, nullptr, nullptr, nullptr, n
 
 KnPeers kn_current_peers() { return g_peers; }
 
-KN_API int kn_output_peers(const uint64_t *peer_y_host, int32_t n) {
-    KN_REQUIRE(n >= 0 && n <= 8, "output_peers: between 0 and 8 peers (got %d)", n);
-    KN_REQUIRE(n == 0 || peer_y_host != nullptr, "output_peers: null pointer list");
-    g_peers.n = n;
-    for (int i = 0; i < 8; i++) g_peers.y[i] = (i < n) ? reinterpret_cast<float *>(peer_y_host[i]) : nullptr;
-    g_peers.row_mask = nullptr;
-    return KN_OK;
+KnPeersScope::KnPeersScope(const kn_peers *p) : saved(g_peers), ok(true) {
+    KnPeers v = {0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr};
+    if (p != nullptr && p->n != 0) {
+        if (p->n < 0 || p->n > 8) { kn_set_error("peers: between 0 and 8 destinations (got %d)", (int)p->n); ok = false; return; }
+        v.n = p->n;
+        for (int i = 0; i < p->n; i++) {
+            if (p->y[i] == 0) { kn_set_error("peers: destination %d is null", i); ok = false; return; }
+            v.y[i] = reinterpret_cast<float *>(p->y[i]);
+        }
+        v.row_mask = p->row_mask;
+    }
+    g_peers = v;
 }
 
-KN_API int kn_output_peers_masked(const uint64_t *peer_y_host, int32_t n, const uint8_t *row_mask) {
-    const int rc = kn_output_peers(peer_y_host, n);
-    if (rc == KN_OK && n > 0) g_peers.row_mask = row_mask;
-    return rc;
-}
+KnPeersScope::~KnPeersScope() { g_peers = saved; }

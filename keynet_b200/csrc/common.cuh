@@ -63,7 +63,16 @@ __device__ __forceinline__ unsigned kn_peer_mask(const KnPeers &peers, int64_t r
     for (unsigned p_ = 0, np_ = ((peers).n > 0 ? (peers).n : 1); p_ < np_; p_++)              \
         if (((mask) >> p_) & 1u)                                                              \
             if (float *dst = ((peers).n > 0 ? (peers).y[p_] : (Y)); true)
-KnPeers kn_current_peers();     // thread-local list set by kn_output_peers() (abi.cu)
+// Every kn_spmm_* entry point takes the destinations as an explicit argument (const kn_peers *, include/keynet_b200.h) and
+// opens a KnPeersScope for the duration of the call; its launch helpers read the validated device-side form back with
+// kn_current_peers().  Nothing survives the call: there is no state shared between calls or threads.
+KnPeers kn_current_peers();
+struct KnPeersScope {
+    KnPeers saved;
+    bool ok;
+    explicit KnPeersScope(const kn_peers *p);
+    ~KnPeersScope();
+};
 
 // number of SMs of the current device (cached); B200 = 148
 int kn_sm_count();

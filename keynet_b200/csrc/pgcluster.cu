@@ -141,7 +141,9 @@ int launch_cluster(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t
 
 KN_API int kn_spmm_cg_f32(const int32_t *cl_gptr, const int32_t *cl_uptr, const int32_t *ucols, const int32_t *rows, const int32_t *lidx, const float *valsT,
                           const int32_t *group_k, const int32_t *block_of, int64_t n_clusters, int32_t G, int32_t K_pad, int32_t u_max, int32_t g_max,
-                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers_arg, void *stream) {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     KN_REQUIRE(n_clusters >= 0 && G > 0 && G <= 256 && K_pad > 0, "spmm_cg: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(g_max > 0 && K_pad % 32 == 0, "spmm_cg: bad g_max / K_pad");
     KN_REQUIRE(u_max > 0 && u_max <= KN_CG_MAX_UNION, "spmm_cg: union of %d columns does not fit the staging tile (max %d)", u_max, KN_CG_MAX_UNION);

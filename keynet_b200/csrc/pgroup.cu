@@ -399,7 +399,9 @@ KN_API int kn_pg_pack(const int64_t *indptr, const int32_t *indices, const float
     return KN_OK;
 }
 
-KN_API int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+KN_API int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const int32_t *rows, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers_arg, void *stream) {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     KN_REQUIRE(S > 0 && G > 0 && n_vecs >= 0 && ldy >= n_vecs, "splitk_reduce: bad shape (S=%d G=%d)", S, G);
     if (n_vecs == 0) return KN_OK;
     KN_REQUIRE(part && rows && Y, "splitk_reduce: null pointer");
@@ -414,7 +416,9 @@ KN_API int kn_splitk_reduce_f32(const float *part, int32_t S, int32_t G, const i
 }
 
 KN_API int kn_spmm_pg_f32(const int32_t *rows, const int32_t *cols, const float *vals, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
-                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+                          const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers_arg, void *stream) {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KT == 0, "spmm_pg: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg: bad leading dimension");
     if (n_groups == 0 || n_vecs == 0) return KN_OK;

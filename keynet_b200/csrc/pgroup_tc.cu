@@ -434,7 +434,9 @@ KN_API int kn_pg_tc_tensormaps(const float *vals_hi, const float *vals_lo, int64
 }
 
 KN_API int kn_spmm_pg_tc_f32(const void *maps_host, const int32_t *rows, const int32_t *cols, const int32_t *group_k, const int32_t *block_of, int64_t n_groups, int32_t G, int32_t K_pad,
-                             const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+                             const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers_arg, void *stream) {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     KN_REQUIRE(n_groups >= 0 && G > 0 && K_pad > 0 && K_pad % KS == 0, "spmm_pg_tc: bad shape (G=%d K_pad=%d)", G, K_pad);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_pg_tc: bad leading dimension");
     if (n_groups == 0 || n_vecs == 0) return KN_OK;

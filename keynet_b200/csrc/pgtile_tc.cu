@@ -37,10 +37,11 @@ constexpr int kMaxT = 6;               // output pixels per tile (issuer warps)
 constexpr int kMaxPos = 32;            // union positions per tile
 constexpr int kMaxStages = 512;
 constexpr int kBiasPos = 255;
+constexpr int kRawStageBytes = KS * BM * 4;      // one gathered stage: 16 rows x 128 batch columns, fp32
 
 struct TileGeom {
     int C, G, Gp, th, tw, T, stride, P, Q, n_taps, uh, uw, U_pos, n_chunks;
-    int n_slots, n_a;                  // weight-slab ring (shared memory) and activation ring (TMEM) depths
+    int n_slots, n_a, n_raw;           // weight-slab ring (shared memory), activation ring (TMEM) and raw gather ring (shared memory) depths
     uint32_t a0;                       // first TMEM column of the activation ring (after the T accumulators)
     int slab_bytes, plane_bytes;
 };
@@ -54,7 +55,8 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sp = smem + (size_t)geo.n_slots * geo.slab_bytes;
+    float *s_raw = reinterpret_cast<float *>(smem + (size_t)geo.n_slots * geo.slab_bytes);          // [n_raw][16 rows][128 batch] gathered fp32
+    unsigned char *sp = smem + (size_t)geo.n_slots * geo.slab_bytes + (size_t)geo.n_raw * kRawStageBytes;
     int32_t *s_cols = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)geo.U_pos * geo.C * 4;
     int32_t *s_tap = reinterpret_cast<int32_t *>(sp);                       sp += (size_t)kMaxT * kMaxPos * 4;     // [t][p] -> tap or -1
     int32_t *s_valid = reinterpret_cast<int32_t *>(sp);                     sp += (size_t)kMaxPos * 4;
@@ -184,71 +186,79 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
     } else if (warp >= kProducerWarp0) {
         // ===== A producers: gather X rows of one (position, channel chunk), split hi/lo, tcgen05.st into the TMEM ring =====
+        // The gathers go through a ring of RAW stages in shared memory filled by cp.async (16 B per lane = one 512 B row
+        // segment per warp instruction): up to n_raw - 1 stages (8 KB each) are in flight per SM, tracked by commit groups.
+        // (Register prefetch -- ld.global into a 4-stage register ring -- ran ONE stage per memory latency, ~1100 cycles:
+        // the loads of all ring stages shared scoreboards, so waiting for the oldest stage waited for the youngest too.)
+        const int pw = warp - kProducerWarp0;                   // producer warp 0..7
         const int q = warp & 3;                                 // TMEM lane quarter
-        const int sel = (warp - kProducerWarp0) >> 2;           // k half of the stage
+        const int sel = pw >> 2;                                // k half of the stage
         constexpr int KW = 8;
-        constexpr int PD = 4;                                   // prefetch distance in stages (register ring)
         const int k0 = sel * KW;
-        const int64_t n = nbase + q * 32 + lane;
-        const bool n_ok = n < n_vecs;
-        const uint64_t xaddr = reinterpret_cast<uint64_t>(X) + (uint64_t)(n_ok ? n : (n_vecs - 1)) * 4ull;
-        const uint32_t ldxb = (uint32_t)ldx * 4u;
-        float buf[PD][KW];
-
-        auto gather = [&](float (&v)[KW], int i) {
-            const int st = s_stage[i];
-            const int cc = st >> 8, p = st & 255;
-            uint32_t cidx[KW];
-            if (p == kBiasPos) {
+        const int n_raw = geo.n_raw;
+        const int64_t ncol = nbase + lane * 4;                  // first batch column of this lane's 16-byte chunk
+        const bool col_ok = ncol < n_vecs;                      // n_vecs % 4 == 0: a chunk is entirely inside or outside
+        const float *__restrict__ xcol = X + (col_ok ? ncol : 0);
+        auto issue_gather = [&](int i) {
+            if (i < n_stages) {
+                const int st = s_stage[i];
+                const int cc = st >> 8, p = st & 255;
+                float *dst = s_raw + (size_t)(i % n_raw) * (KS * BM);
 #pragma unroll
-                for (int j = 0; j < KW; j++) cidx[j] = (uint32_t)bias_col;
-            } else {
-                const int4 *cp = reinterpret_cast<const int4 *>(s_cols + p * C + cc * KS + k0);      // 16-byte aligned: C % 16 == 0
-                const int4 c0 = cp[0], c1 = cp[1];
-                cidx[0] = (uint32_t)c0.x; cidx[1] = (uint32_t)c0.y; cidx[2] = (uint32_t)c0.z; cidx[3] = (uint32_t)c0.w;
-                cidx[4] = (uint32_t)c1.x; cidx[5] = (uint32_t)c1.y; cidx[6] = (uint32_t)c1.z; cidx[7] = (uint32_t)c1.w;
+                for (int rr = 0; rr < 2; rr++) {
+                    const int r = pw * 2 + rr;                  // row of the stage handled by this warp
+                    const int32_t c = (p == kBiasPos) ? bias_col : s_cols[p * C + cc * KS + r];
+                    const float *src = xcol + (int64_t)c * ldx;
+                    const unsigned d32 = smem_u32(dst + r * BM + lane * 4);
+                    const int bytes = col_ok ? 16 : 0;          // src-size 0 => 16 bytes of zeros
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d32), "l"(src), "r"(bytes));
+                }
             }
-#pragma unroll
-            for (int j = 0; j < KW; j++) {
-                uint64_t a;
-                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cidx[j]), "r"(ldxb), "l"(xaddr));
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v[j]) : "l"(a));
-            }
+            asm volatile("cp.async.commit_group;\n" ::);
         };
         int psa = 0; uint32_t ppa = 0;
-        auto publish = [&](const float (&v)[KW]) {
+        for (int i = 0; i < n_raw - 1; i++) issue_gather(i);
+        for (int i = 0; i < n_stages; i++) {
+            // stage i has landed for this thread's copies; the barrier makes every producer's copies visible and tells that
+            // all of them are done reading stage i-1, whose slot the next gather overwrites
+            switch (n_raw - 2) {
+                case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+                case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+                case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+                case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+                case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+                case 6: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
+                case 7: asm volatile("cp.async.wait_group 7;\n" ::: "memory"); break;
+                case 8: asm volatile("cp.async.wait_group 8;\n" ::: "memory"); break;
+                case 9: asm volatile("cp.async.wait_group 9;\n" ::: "memory"); break;
+                case 10: asm volatile("cp.async.wait_group 10;\n" ::: "memory"); break;
+                case 11: asm volatile("cp.async.wait_group 11;\n" ::: "memory"); break;
+                case 12: asm volatile("cp.async.wait_group 12;\n" ::: "memory"); break;
+                case 13: asm volatile("cp.async.wait_group 13;\n" ::: "memory"); break;
+                case 14: asm volatile("cp.async.wait_group 14;\n" ::: "memory"); break;
+                default: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            issue_gather(i + n_raw - 1);
+            const float *src = s_raw + (size_t)(i % n_raw) * (KS * BM) + q * 32 + lane;
             uint32_t hi[KW], lo[KW];
 #pragma unroll
-            for (int i = 0; i < KW; i++) {
-                hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-                lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+            for (int j = 0; j < KW; j++) {
+                const float v = src[(k0 + j) * BM];
+                hi[j] = __float_as_uint(v) & 0xFFFFE000u;
+                lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
             }
             mbar_wait(&emptyA[psa], ppa ^ 1u);
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + geo.a0 + (uint32_t)(psa * 32 + k0);
             tmem_store<KW>(ta, hi);
             tmem_store<KW>(ta + 16, lo);
-        };
-        auto finish = [&]() {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&fullA[psa]);
             if (++psa == geo.n_a) { psa = 0; ppa ^= 1u; }
-        };
-#pragma unroll
-        for (int dd = 0; dd < PD; dd++)
-            if (dd < n_stages) gather(buf[dd], dd);
-        for (int i0 = 0; i0 < n_stages; i0 += PD) {
-#pragma unroll
-            for (int dd = 0; dd < PD; dd++) {
-                const int i = i0 + dd;
-                if (i < n_stages) {
-                    publish(buf[dd]);
-                    if (i + PD < n_stages) gather(buf[dd], i + PD);
-                    finish();
-                }
-            }
         }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 
         // ===== epilogue: TMEM -> registers -> ReLU -> Y rows of every pixel of the tile =====
         mbar_wait(accum_bar, 0);
@@ -361,7 +371,9 @@ KN_API int kn_conv2d_tiles_index(const kn_conv2d_desc *desc, const int32_t *tile
 
 KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, const int32_t *tile_rows, int32_t bias_col, int64_t n_tiles,
                                int32_t C, int32_t G, int32_t th, int32_t tw, int32_t stride, int32_t P, int32_t Q,
-                               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, void *stream) {
+                               const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers_arg, void *stream) {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     KN_REQUIRE(n_tiles >= 0 && C > 0 && C % KS == 0 && G > 0 && th > 0 && tw > 0 && stride > 0 && P > 0 && Q > 0, "spmm_tile_tc: bad shape (C=%d G=%d)", C, G);
     KN_REQUIRE(n_vecs >= 0 && ldx >= n_vecs && ldy >= n_vecs, "spmm_tile_tc: bad leading dimension");
     if (n_tiles == 0 || n_vecs == 0) return KN_OK;
@@ -380,12 +392,19 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     g.plane_bytes = g.Gp * KS * 4;
     g.slab_bytes = 2 * g.plane_bytes;
     const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * kMaxPos * 4 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
-    int n_slots = (int)((226 * 1024 - (int64_t)fixed) / g.slab_bytes);
+    const int64_t avail = 226 * 1024 - (int64_t)fixed;
+    // shared memory: the weight slabs of at least one channel chunk (+1 so the next chunk can start loading), the rest split
+    // between the raw gather ring (bytes in flight towards this SM) and more weight slabs
+    int n_raw = (int)((avail - (int64_t)(g.n_taps + 1) * g.slab_bytes) / kRawStageBytes);
+    if (n_raw > 16) n_raw = 16;
+    KN_REQUIRE(n_raw >= 3, "spmm_tile_tc: the weight slabs of one channel chunk do not fit shared memory (Gp=%d taps=%d)", g.Gp, g.n_taps);
+    int n_slots = (int)((avail - (int64_t)n_raw * kRawStageBytes) / g.slab_bytes);
     if (n_slots > 3 * g.n_taps) n_slots = 3 * g.n_taps;
     KN_REQUIRE(n_slots >= g.n_taps + 1, "spmm_tile_tc: the weight slabs of one channel chunk do not fit shared memory (Gp=%d taps=%d)", g.Gp, g.n_taps);
     KN_REQUIRE((size_t)(2 * n_slots + 2 * g.n_a + 2) * 8 <= 1024, "spmm_tile_tc: too many barriers");
     g.n_slots = n_slots;
-    const size_t smem = (size_t)n_slots * g.slab_bytes + fixed;
+    g.n_raw = n_raw;
+    const size_t smem = (size_t)n_slots * g.slab_bytes + (size_t)n_raw * kRawStageBytes + fixed;
     const int64_t n_btiles = kn_cdiv(n_vecs, BM);
     KN_REQUIRE(n_tiles * n_btiles <= 0x7fffffffLL, "spmm_tile_tc: grid too large");
     KN_ONCE_PER_DEVICE {

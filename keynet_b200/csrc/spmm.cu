@@ -301,15 +301,19 @@ static int spmm_csr_impl(const int64_t *indptr, const int32_t *indices, const fl
 KN_API int kn_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *data,
                            int64_t n_rows, int64_t n_cols,
                            const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
-                           uint32_t flags, void *stream)
+                           uint32_t flags, const kn_peers *peers_arg, void *stream)
 {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     return spmm_csr_impl(indptr, indices, data, n_rows, n_cols, nullptr, X, ldx, Y, ldy, n_vecs, flags, stream);
 }
 
 KN_API int kn_spmm_csr_rows_f32(const int64_t *indptr, const int32_t *indices, const float *data,
                                 int64_t n_rows, int64_t n_cols, const int32_t *out_rows,
                                 const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs,
-                                uint32_t flags, void *stream)
+                                uint32_t flags, const kn_peers *peers_arg, void *stream)
 {
+    KnPeersScope peers_scope(peers_arg);
+    if (!peers_scope.ok) return KN_ERR_INVALID_ARGUMENT;
     return spmm_csr_impl(indptr, indices, data, n_rows, n_cols, out_rows, X, ldx, Y, ldy, n_vecs, flags, stream);
 }

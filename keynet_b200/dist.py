@@ -109,9 +109,9 @@ class ShardedKeyedModel(object):
 
     def __init__(self, inshape, net, rank, world, group=None, fused=False, selective=True, keep_csr=True, **keynet_kwargs):
         """fused=True: no NCCL on the data path -- every SpMM epilogue stores its rows straight into all ranks' gathered
-        activation buffers (torch symmetric memory = NVLink peer mappings, kn_output_peers), one device-side barrier per
+        activation buffers (torch symmetric memory = NVLink peer mappings, the `kn_peers` argument of every kn_spmm_*), one device-side barrier per
         layer; with selective=True (default) a row is stored only into the buffers of the ranks whose next layer reads it
-        (kn_output_peers_masked).  fused=False: local SpMM + torch.distributed all_gather_into_tensor (NCCL)."""
+        (kn_peers.row_mask).  fused=False: local SpMM + torch.distributed all_gather_into_tensor (NCCL)."""
         from . import system
         self.rank, self.world, self.group = int(rank), int(world), group
         self.fused = bool(fused)
@@ -197,11 +197,8 @@ class ShardedKeyedModel(object):
             n_mine = len(sh.my_rows)
             slot = self.rank * sh.chunk * N * 4                         # byte offset of this rank's slot in every buffer
             if n_mine > 0:
-                _native.set_output_peers([int(p) + slot for p in h.buffer_ptrs], masks[k])
-                try:
-                    spmm(L.W, X, relu=relu, out=Yfull[self.rank * sh.chunk:self.rank * sh.chunk + n_mine])
-                finally:
-                    _native.set_output_peers([])
+                peers = _native.Peers([int(p) + slot for p in h.buffer_ptrs], masks[k])
+                spmm(L.W, X, relu=relu, out=Yfull[self.rank * sh.chunk:self.rank * sh.chunk + n_mine], peers=peers)
             Yfull[-1].fill_(1.0)                                        # homogeneous coordinate: local
             self._stamp()
             h.barrier()                                                 # every rank's stores have landed everywhere

@@ -1101,42 +1101,39 @@ class PatternGroups(object):
         return dict(n_clusters=n_cl, u_max=u_max, g_max=g_max, cl_gptr=cl_gptr.to(torch.int32), cl_uptr=cl_uptr.to(torch.int32), ucols=(uniq % int(n_cols)).to(torch.int32),
                     lidx=lidx, valsT=vT.contiguous())
 
-    def spmm(self, x, y, relu):
+    def spmm(self, x, y, relu, peers=None):
+        """peers: _native.Peers (the output slot on every rank + need mask, dist.py) or None for plain stores to y."""
         L = _native.lib()
         N = x.shape[1]
         flags = _native.KN_SPMM_RELU if relu else 0
+        pp = _native.peers_arg(peers)
         for c in self.classes:
             cg = c.get('cg')
             if cg is not None and clusters_enabled():
                 check(L.kn_spmm_cg_f32(ptr(cg['cl_gptr']), ptr(cg['cl_uptr']), ptr(cg['ucols']), ptr(c['rows']), ptr(cg['lidx']), ptr(cg['valsT']), ptr(c['group_k']), ptr(c['block_of']),
-                                       cg['n_clusters'], c['G'], c['K_pad'], cg['u_max'], cg['g_max'], ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+                                       cg['n_clusters'], c['G'], c['K_pad'], cg['u_max'], cg['g_max'], ptr(x), N, ptr(y), N, N, flags, pp, stream_ptr()))
             elif c.get('splitk') is not None and N >= PatternGroups.TC_MIN_BATCH and N <= PatternGroups.SPLITK_MAX_BATCH and tensor_cores_enabled():
                 k = c['splitk']
                 part = k['part'].get(N)
                 if part is None:
                     part = k['part'][N] = torch.empty((k['S'] * k['G'], N), dtype=torch.float32, device=x.device)
-                saved = _native.current_output_peers()
-                if saved[0]:
-                    _native.set_output_peers([])                      # the partial rows are local scratch
                 check(L.kn_spmm_pg_tc_f32(k['tc']['maps'], ptr(k['rows']), ptr(k['cols']), ptr(k['group_k']), None, k['S'], k['G'], k['K_pad'],
-                                          ptr(x), N, ptr(part), N, N, 0, stream_ptr()))
-                if saved[0]:
-                    _native.set_output_peers(*saved)
-                check(L.kn_splitk_reduce_f32(ptr(part), k['S'], k['G'], ptr(c['rows']), ptr(y), N, N, flags, stream_ptr()))
+                                          ptr(x), N, ptr(part), N, N, 0, None, stream_ptr()))       # the partial rows are local scratch
+                check(L.kn_splitk_reduce_f32(ptr(part), k['S'], k['G'], ptr(c['rows']), ptr(y), N, N, flags, pp, stream_ptr()))
             elif c.get('tile') is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled() and tiles_enabled():
                 t = c['tile']
                 check(L.kn_spmm_tile_tc_f32(t['maps'], ptr(t['cols']), ptr(t['rows']), t['bias_col'], t['n_tiles'], t['C'], t['G'], t['th'], t['tw'], t['stride'], t['P'], t['Q'],
-                                            ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+                                            ptr(x), N, ptr(y), N, N, flags, pp, stream_ptr()))
             elif c['tc'] is not None and N >= PatternGroups.TC_MIN_BATCH and tensor_cores_enabled():
                 check(L.kn_spmm_pg_tc_f32(c['tc']['maps'], ptr(c['rows']), ptr(c['cols']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
-                                          ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+                                          ptr(x), N, ptr(y), N, N, flags, pp, stream_ptr()))
             else:
                 check(L.kn_spmm_pg_f32(ptr(c['rows']), ptr(c['cols']), ptr(c['vals']), ptr(c['group_k']), ptr(c['block_of']), c['n_groups'], c['G'], c['K_pad'],
-                                       ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+                                       ptr(x), N, ptr(y), N, N, flags, pp, stream_ptr()))
         r = self.rest
         if r is not None:
             check(L.kn_spmm_csr_rows_f32(ptr(r['indptr']), ptr(r['indices']), ptr(r['data']), r['n'], self.shape[1], ptr(r['out_rows']),
-                                         ptr(x), N, ptr(y), N, N, flags, stream_ptr()))
+                                         ptr(x), N, ptr(y), N, N, flags, pp, stream_ptr()))
 
     def launches(self):
         return sum(2 if c.get('splitk') is not None else 1 for c in self.classes) + (1 if self.rest is not None else 0)
@@ -1149,22 +1146,23 @@ class PatternGroups(object):
 # =============================================================================================
 # SpMM
 # =============================================================================================
-def spmm(W, x, relu=False, out=None):
-    """y[R, N] = W . x[C, N] (+ReLU) on the current CUDA stream.  x: contiguous float32 CUDA tensor."""
+def spmm(W, x, relu=False, out=None, peers=None):
+    """y[R, N] = W . x[C, N] (+ReLU) on the current CUDA stream.  x: contiguous float32 CUDA tensor.
+    peers (_native.Peers): store every output row into the same slot of several ranks' buffers instead (fused all-gather)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.ndim == 2 and x.is_contiguous()
     assert x.shape[0] == W.shape[1], "Non-conformal shape for W=%s, x=%s" % (str(W.shape), str(tuple(x.shape)))
     (R, N) = (W.shape[0], x.shape[1])
     y = out if out is not None else torch.empty((R, N), dtype=torch.float32, device=x.device)
     assert y.shape == (R, N) and y.is_contiguous()
     if W._pg is not None and N >= 32 and N % 4 == 0:
-        W._pg.spmm(x, y, relu)
+        W._pg.spmm(x, y, relu, peers)
         return y
     if W._data is None:
         # CSR was dropped (drop_csr): narrow / ragged batches are padded to the grouped kernels' granularity
         Np = max(32, (N + 3) // 4 * 4)
         # the grouped kernels would store into the peers' buffers with leading dimension Np: the fused row-sharded path
         # must pad its batch itself (dist.ShardedKeyedModel does)
-        assert not _native.current_output_peers()[0], 'ragged batch on a dropped-CSR matrix while output peers are set'
+        assert peers is None, 'ragged batch on a dropped-CSR matrix with output peers: the fused row-sharded path pads its batch itself'
         xp = torch.zeros((x.shape[0], Np), dtype=torch.float32, device=x.device)
         xp[:, :N] = x
         yp = torch.empty((R, Np), dtype=torch.float32, device=x.device)
@@ -1172,7 +1170,7 @@ def spmm(W, x, relu=False, out=None):
         y.copy_(yp[:, :N])
         return y
     check(_native.lib().kn_spmm_csr_f32(ptr(W._indptr), ptr(W._indices), ptr(W._data), R, W.shape[1],
-                                        ptr(x), N, ptr(y), N, N, _native.KN_SPMM_RELU if relu else 0, stream_ptr()))
+                                        ptr(x), N, ptr(y), N, N, _native.KN_SPMM_RELU if relu else 0, _native.peers_arg(peers), stream_ptr()))
     return y
 
 
@@ -1451,8 +1449,8 @@ def _conv_tiles(desc, geom, wq, bq, pix_np, row_of_src, col_map, bias_col, dev):
     if Uo % th != 0 or Vo % tw != 0 or uh * uw > 32 or th * tw * Gp + 4 * 32 > 512:
         return None
     slab = 2 * Gp * 64
-    if (226 * 1024 - (uh * uw * C * 4 + 4096)) // slab < P * Q + 1:
-        return None
+    if (226 * 1024 - (uh * uw * C * 4 + 4096) - (P * Q + 1) * slab) // 8192 < 3:
+        return None                                   # weight slabs of a channel chunk + a raw gather ring must fit shared memory
     (py, px) = (pix_np // Vo, pix_np % Vo)
     origin = (py // th * th) * Vo + (px // tw * tw)
     (tiles, counts) = np.unique(origin, return_counts=True)

@@ -53,9 +53,9 @@ int main() {
     long long *d; cudaMalloc(&d, 8); long long h;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     int iters = 4096;
-    for (int at = 0; at < 2; at++) for (int N : {32, 96, 192, 256}) for (int nacc : {1, 2, 4}) {
+    for (int at = 0; at < 2; at++) for (int N : {32, 64, 96, 128, 192, 256}) for (int nacc : {1, 2, 3, 4}) {
         if (nacc * N > 448) continue;
-        k<<<148, 160, 64 * 1024>>>(d, N, at, iters, 0, nacc);
+        k<<<148, 192, 64 * 1024>>>(d, N, at, iters, 0, nacc);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
         printf("tf32 A=%s N=%3d issuers=%d: %s %.1f cycles per MMA per issuer\n", at ? "tmem" : "smem", N, nacc, cudaGetErrorString(e), (double)h / iters);

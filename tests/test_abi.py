@@ -1,4 +1,5 @@
 """The C-ABI library loads on a CPU-only box and exports exactly the symbols include/keynet_b200.h declares."""
+import ctypes
 import os
 import re
 
@@ -30,7 +31,7 @@ def test_library_exports_every_declared_symbol(built):
     L = built.lib()
     for s in _header_symbols():
         assert hasattr(L, s), s
-    assert L.kn_abi_version() == 1
+    assert L.kn_abi_version() == 2
 
 
 def test_header_cites_reference_interfaces():
@@ -43,10 +44,13 @@ def test_header_cites_reference_interfaces():
 def test_argument_validation_without_gpu(built):
     """Invalid arguments are rejected with an error code and a message before any CUDA work."""
     L = built.lib()
-    rc = L.kn_spmm_csr_f32(None, None, None, 4, 4, None, 1, None, 1, 2, 0, None)     # ld < n_vecs
+    rc = L.kn_spmm_csr_f32(None, None, None, 4, 4, None, 1, None, 1, 2, 0, None, None)     # ld < n_vecs
     assert rc == -1 and b'leading dimension' in L.kn_last_error()
     rc = L.kn_exclusive_scan_i64(None, None, -1, None)
     assert rc == -1
+    bad = built.kn_peers(); bad.n = 9                                                  # more than 8 destinations
+    rc = L.kn_spmm_csr_f32(None, None, None, 4, 4, None, 2, None, 2, 2, 0, ctypes.byref(bad), None)
+    assert rc == -1 and b'destinations' in L.kn_last_error()
     d = built.kn_conv2d_desc(1, 8, 8, 1, 2, 2, 1, 0, 1)                               # even kernel
     rc = L.kn_toeplitz_conv2d_count(d, None, 1, None, None)
     assert rc == -1 and b'odd' in L.kn_last_error()

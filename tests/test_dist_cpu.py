@@ -109,7 +109,7 @@ def _worker(rank, world, port, q):
             Yfull[-1] = 1.0
             X = Yfull.numpy()
             if k + 1 < len(layers):
-                # selective peer stores (kn_output_peers_masked): a rank only ever receives the rows its next layer reads.
+                # selective peer stores (kn_peers.row_mask): a rank only ever receives the rows its next layer reads.
                 # Emulated by poisoning everything else after the gather -- the result must not change.
                 need = np.zeros(sh.n_phys, dtype=bool)
                 need[Wls[k + 1].indices] = True

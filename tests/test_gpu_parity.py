@@ -86,7 +86,7 @@ def test_spmm_edge_cases():
     # aliasing X and Y is rejected by the ABI
     x = torch.zeros(20, 16, device='cuda')
     rc = _native.lib().kn_spmm_csr_f32(_native.ptr(W._indptr), _native.ptr(W._indices), _native.ptr(W._data), 20, 20,
-                                       _native.ptr(x), 16, _native.ptr(x), 16, 16, 0, None)
+                                       _native.ptr(x), 16, _native.ptr(x), 16, 16, 0, None, None)
     assert rc == -1
 
 
