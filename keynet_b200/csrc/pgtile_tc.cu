@@ -28,16 +28,28 @@
 namespace {
 using namespace kn_tc;
 
-constexpr int kThreads = 512;          // warp 0: TMA (weight slabs)  warps 1-6: MMA issuers  warp 7: TMEM alloc  warps 8-15: A producers + epilogue
-constexpr int kProducerThreads = 256;
+constexpr int kThreads = 512;          // warp 0: TMA (weight slabs)  warps 1-4: MMA issuers  warps 5-6: activation gathers (cp.async)  warp 7: TMEM alloc  warps 8-15: hi/lo splitters + epilogue
+constexpr int kGroupThreads = 128;     // the 8 splitter warps work as two groups of 4 (one warp per TMEM lane quarter) on alternate stages
 constexpr int kProducerWarp0 = 8;
 constexpr int KS = 16;                 // k per stage = channels per chunk
 constexpr int BM = 128;                // batch columns per CTA (UMMA M)
-constexpr int kMaxT = 6;               // output pixels per tile (issuer warps)
+constexpr int kMaxT = 4;               // output pixels per tile (issuer warps 1-4)
+constexpr int kGatherWarp0 = 5;        // warps 5, 6: activation gathers (alternate stages)
 constexpr int kMaxPos = 32;            // union positions per tile
 constexpr int kMaxStages = 512;
 constexpr int kBiasPos = 255;
 constexpr int kRawStageBytes = KS * BM * 4;      // one gathered stage: 16 rows x 128 batch columns, fp32
+
+#ifdef KN_TILE_PROF
+__device__ long long g_tile_prof[64];
+#define PROF_T0() const long long pt0_ = clock64()
+#define PROF_ADD(slot) do { if (blockIdx.x == 5000) atomicAdd((unsigned long long *)&g_tile_prof[slot], (unsigned long long)(clock64() - pt0_)); } while (0)
+#define PROF_SET(slot) do { if (blockIdx.x == 5000) g_tile_prof[slot] = clock64(); } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#define PROF_SET(slot)
+#endif
 
 struct TileGeom {
     int C, G, Gp, th, tw, T, stride, P, Q, n_taps, uh, uw, U_pos, n_chunks;
@@ -58,6 +70,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     float *s_raw = reinterpret_cast<float *>(smem + (size_t)geo.n_slots * geo.slab_bytes);          // [n_raw][16 rows][128 batch] gathered fp32
     unsigned char *sp = smem + (size_t)geo.n_slots * geo.slab_bytes + (size_t)geo.n_raw * kRawStageBytes;
     int32_t *s_cols = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)geo.U_pos * geo.C * 4;
+    int32_t *s_rows = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)kMaxT * 256 * 4;         // [t][G] output rows of the tile
     int32_t *s_tap = reinterpret_cast<int32_t *>(sp);                       sp += (size_t)kMaxT * kMaxPos * 4;     // [t][p] -> tap or -1
     int32_t *s_valid = reinterpret_cast<int32_t *>(sp);                     sp += (size_t)kMaxPos * 4;
     uint16_t *s_stage = reinterpret_cast<uint16_t *>(sp);                   sp += (size_t)kMaxStages * 2;         // (chunk << 8) | position
@@ -66,10 +79,13 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     uint64_t *emptyB = fullB + geo.n_slots;
     uint64_t *fullA = emptyB + geo.n_slots;
     uint64_t *emptyA = fullA + geo.n_a;
-    uint64_t *accum_bar = emptyA + geo.n_a;
+    uint64_t *raw_full = emptyA + geo.n_a;
+    uint64_t *raw_empty = raw_full + geo.n_raw;
+    uint64_t *accum_bar = raw_empty + geo.n_raw;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) PROF_SET(0);
     const KnRaster rt = kn_raster(blockIdx.x, n_sp_tiles, n_btiles, super_tiles);
     const int64_t tile = rt.item;
     const int64_t nbase = rt.tile * BM;
@@ -77,7 +93,8 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < geo.n_slots; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], T); }
-        for (int s = 0; s < geo.n_a; s++) { mbar_init(&fullA[s], kProducerThreads); mbar_init(&emptyA[s], T); }
+        for (int s = 0; s < geo.n_a; s++) { mbar_init(&fullA[s], kGroupThreads); mbar_init(&emptyA[s], T); }
+        for (int s = 0; s < geo.n_raw; s++) { mbar_init(&raw_full[s], 32); mbar_init(&raw_empty[s], kGroupThreads); }
         mbar_init(accum_bar, T);
         fence_barrier_init();
     } else if (warp == 7) {
@@ -87,6 +104,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     // the tile's gather table, the (pixel, position) -> tap table and the list of in-image stages
     const int32_t *__restrict__ tc = tile_cols + tile * (int64_t)U_pos * C;
     for (int i = tid; i < U_pos * C; i += kThreads) s_cols[i] = __ldg(tc + i);
+    for (int i = tid; i < T * geo.G; i += kThreads) s_rows[(i / geo.G) * 256 + (i % geo.G)] = __ldg(tile_rows + tile * (int64_t)T * geo.G + i);
     for (int i = tid; i < kMaxT * kMaxPos; i += kThreads) {
         const int t = i / kMaxPos, p = i - t * kMaxPos;
         int tap = -1;
@@ -99,19 +117,25 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
     if (tid < kMaxPos) s_valid[tid] = (tid < U_pos && __ldg(tc + (int64_t)tid * C) >= 0) ? 1 : 0;
     __syncthreads();
-    if (tid == 0) {
-        int n = 0;
-        for (int cc = 0; cc < geo.n_chunks; cc++)
-            for (int p = 0; p < U_pos; p++)
-                if (s_valid[p]) s_stage[n++] = (uint16_t)((cc << 8) | p);
-        s_stage[n++] = (uint16_t)((geo.n_chunks << 8) | kBiasPos);          // bias: the homogeneous row against the bias slab
-        *s_nstages = n;
+    {   // list of in-image stages, chunk-major: stage index = chunk * n_valid + rank of the position among the valid ones
+        unsigned vmask = 0;
+        for (int p = 0; p < U_pos; p++) vmask |= (s_valid[p] ? 1u : 0u) << p;
+        const int n_valid = __popc(vmask);
+        for (int i = tid; i < geo.n_chunks * U_pos; i += kThreads) {
+            const int cc = i / U_pos, p = i - cc * U_pos;
+            if ((vmask >> p) & 1u) s_stage[cc * n_valid + __popc(vmask & ((1u << p) - 1u))] = (uint16_t)((cc << 8) | p);
+        }
+        if (tid == 0) {
+            s_stage[geo.n_chunks * n_valid] = (uint16_t)((geo.n_chunks << 8) | kBiasPos);    // bias: the homogeneous row against the bias slab
+            *s_nstages = geo.n_chunks * n_valid + 1;
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_stages = *s_nstages;
+    if (tid == 0) PROF_SET(1);
     const int n_slabs = geo.n_chunks * geo.n_taps + 1;
 
     if (warp == 0) {
@@ -159,13 +183,15 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     int slot = 0; uint32_t pb = 0;
                     if (tap >= 0) {
                         slab_of(cc * geo.n_taps + tap, slot, pb);
-                        mbar_wait(&fullB[slot], pb);
+                        { PROF_T0(); mbar_wait(&fullB[slot], pb); if (t == 0) PROF_ADD(10); }
                     }
                     if (valid) {
-                        mbar_wait(&fullA[sa], pa);
+                        { PROF_T0(); mbar_wait(&fullA[sa], pa); if (t == 0) PROF_ADD(11); }
                         tc_fence_after();
+                        { PROF_T0();
                         if (tap >= 0) { issue(slot); umma_commit(&emptyB[slot]); }
                         umma_commit(&emptyA[sa]);
+                        if (t == 0) PROF_ADD(12); }
                         if (++sa == geo.n_a) { sa = 0; pa ^= 1u; }
                     } else if (tap >= 0) {
                         mbar_arrive(&emptyB[slot]);                // tap outside the image: release the slab unused
@@ -183,90 +209,92 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 umma_commit(&emptyA[sa]);
             }
             umma_commit(accum_bar);
+            if (t == 0) PROF_SET(2);
         }
-    } else if (warp >= kProducerWarp0) {
-        // ===== A producers: gather X rows of one (position, channel chunk), split hi/lo, tcgen05.st into the TMEM ring =====
-        // The gathers go through a ring of RAW stages in shared memory filled by cp.async (16 B per lane = one 512 B row
-        // segment per warp instruction): up to n_raw - 1 stages (8 KB each) are in flight per SM, tracked by commit groups.
-        // (Register prefetch -- ld.global into a 4-stage register ring -- ran ONE stage per memory latency, ~1100 cycles:
-        // the loads of all ring stages shared scoreboards, so waiting for the oldest stage waited for the youngest too.)
-        const int pw = warp - kProducerWarp0;                   // producer warp 0..7
-        const int q = warp & 3;                                 // TMEM lane quarter
-        const int sel = pw >> 2;                                // k half of the stage
-        constexpr int KW = 8;
-        const int k0 = sel * KW;
-        const int n_raw = geo.n_raw;
+    } else if (warp == kGatherWarp0 || warp == kGatherWarp0 + 1) {
+        // ===== gather warps (alternate stages): X rows of every (position, channel chunk) stage into the raw ring, cp.async 16 B per lane =====
+        // One warp instruction copies one 512 B row segment; the 16 rows of a stage complete on the stage's mbarrier
+        // (cp.async.mbarrier.arrive.noinc from every lane).  Up to n_raw stages (8 KB each) are in flight towards this SM,
+        // independent of the splitters' progress.  (Register prefetch -- ld.global into a ring of registers -- ran ONE stage
+        // per memory latency, and a lock-step copy / split loop ~1500 cycles per stage: both far below the tensor pipe.)
         const int64_t ncol = nbase + lane * 4;                  // first batch column of this lane's 16-byte chunk
         const bool col_ok = ncol < n_vecs;                      // n_vecs % 4 == 0: a chunk is entirely inside or outside
         const float *__restrict__ xcol = X + (col_ok ? ncol : 0);
-        auto issue_gather = [&](int i) {
-            if (i < n_stages) {
-                const int st = s_stage[i];
-                const int cc = st >> 8, p = st & 255;
-                float *dst = s_raw + (size_t)(i % n_raw) * (KS * BM);
+        const int bytes = col_ok ? 16 : 0;                      // src-size 0 => 16 bytes of zeros
+        for (int i = warp - kGatherWarp0; i < n_stages; i += 2) {
+            const int st = s_stage[i];
+            const int cc = st >> 8, p = st & 255;
+            const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
+            { PROF_T0(); mbar_wait(&raw_empty[slot], (uint32_t)((wr & 1) ^ 1)); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
+            PROF_T0();
+            float *dst = s_raw + (size_t)slot * (KS * BM) + lane * 4;
+            // the 16 row indices first (4 x LDS.128), then 16 back-to-back copies: an index load in front of every copy
+            // serialised the warp at ~75 cycles per copy (1200 cycles per stage, measured) instead of the LSU's ~8
+            int32_t cidx[KS];
+            if (p == kBiasPos) {
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const int r = pw * 2 + rr;                  // row of the stage handled by this warp
-                    const int32_t c = (p == kBiasPos) ? bias_col : s_cols[p * C + cc * KS + r];
-                    const float *src = xcol + (int64_t)c * ldx;
-                    const unsigned d32 = smem_u32(dst + r * BM + lane * 4);
-                    const int bytes = col_ok ? 16 : 0;          // src-size 0 => 16 bytes of zeros
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d32), "l"(src), "r"(bytes));
+                for (int r = 0; r < KS; r++) cidx[r] = bias_col;
+            } else {
+                const int4 *cp4 = reinterpret_cast<const int4 *>(s_cols + p * C + cc * KS);     // 64-byte aligned: C % 16 == 0
+#pragma unroll
+                for (int r4 = 0; r4 < KS / 4; r4++) {
+                    const int4 c = cp4[r4];
+                    cidx[4 * r4 + 0] = c.x; cidx[4 * r4 + 1] = c.y; cidx[4 * r4 + 2] = c.z; cidx[4 * r4 + 3] = c.w;
                 }
             }
-            asm volatile("cp.async.commit_group;\n" ::);
-        };
-        int psa = 0; uint32_t ppa = 0;
-        for (int i = 0; i < n_raw - 1; i++) issue_gather(i);
-        for (int i = 0; i < n_stages; i++) {
-            // stage i has landed for this thread's copies; the barrier makes every producer's copies visible and tells that
-            // all of them are done reading stage i-1, whose slot the next gather overwrites
-            switch (n_raw - 2) {
-                case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
-                case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
-                case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
-                case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
-                case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
-                case 6: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
-                case 7: asm volatile("cp.async.wait_group 7;\n" ::: "memory"); break;
-                case 8: asm volatile("cp.async.wait_group 8;\n" ::: "memory"); break;
-                case 9: asm volatile("cp.async.wait_group 9;\n" ::: "memory"); break;
-                case 10: asm volatile("cp.async.wait_group 10;\n" ::: "memory"); break;
-                case 11: asm volatile("cp.async.wait_group 11;\n" ::: "memory"); break;
-                case 12: asm volatile("cp.async.wait_group 12;\n" ::: "memory"); break;
-                case 13: asm volatile("cp.async.wait_group 13;\n" ::: "memory"); break;
-                case 14: asm volatile("cp.async.wait_group 14;\n" ::: "memory"); break;
-                default: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
-            }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            issue_gather(i + n_raw - 1);
-            const float *src = s_raw + (size_t)(i % n_raw) * (KS * BM) + q * 32 + lane;
-            uint32_t hi[KW], lo[KW];
+            const uint32_t d32 = smem_u32(dst);
 #pragma unroll
-            for (int j = 0; j < KW; j++) {
-                const float v = src[(k0 + j) * BM];
+            for (int r = 0; r < KS; r++) {
+                const float *src = xcol + (int64_t)cidx[r] * ldx;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d32 + (uint32_t)(r * BM * 4)), "l"(src), "r"(bytes));
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&raw_full[slot])) : "memory");
+            if (tid == kGatherWarp0 * 32) PROF_ADD(31);
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else if (warp >= kProducerWarp0) {
+        // ===== splitters: raw stage -> hi / lo TF32 planes -> tcgen05.st into the TMEM ring =====
+        // two groups of four warps (one warp per TMEM lane quarter) take alternate stages, so the fixed latencies of one
+        // stage's chain (barrier wait, shared-memory reads, TMEM store + wait, arrive) overlap with the other group's stage
+        const int q = warp & 3;                                 // TMEM lane quarter
+        const int sel = (warp - kProducerWarp0) >> 2;           // splitter group
+        const float *src0 = s_raw + q * 32 + lane;
+        for (int i = sel; i < n_stages; i += 2) {
+            const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
+            const int wa = i / geo.n_a, sa = i - wa * geo.n_a;
+            { PROF_T0(); mbar_wait(&raw_full[slot], (uint32_t)(wr & 1)); if (tid == 256) PROF_ADD(20); }
+            const float *src = src0 + (size_t)slot * (KS * BM);
+            uint32_t hi[KS], lo[KS];
+            { PROF_T0();
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                const float v = src[j * BM];
                 hi[j] = __float_as_uint(v) & 0xFFFFE000u;
                 lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
             }
-            mbar_wait(&emptyA[psa], ppa ^ 1u);
+            mbar_arrive(&raw_empty[slot]);                      // the values are in registers: the slot can be refilled
+            if (tid == 256) PROF_ADD(21); }
+            { PROF_T0(); mbar_wait(&emptyA[sa], (uint32_t)((wa & 1) ^ 1)); if (tid == 256) PROF_ADD(23); }
             tc_fence_after();
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + geo.a0 + (uint32_t)(psa * 32 + k0);
-            tmem_store<KW>(ta, hi);
-            tmem_store<KW>(ta + 16, lo);
+            PROF_T0();
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + geo.a0 + (uint32_t)(sa * 32);
+            tmem_store<KS>(ta, hi);
+            tmem_store<KS>(ta + 16, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(&fullA[psa]);
-            if (++psa == geo.n_a) { psa = 0; ppa ^= 1u; }
+            mbar_arrive(&fullA[sa]);
+            if (tid == 256) PROF_ADD(24);
         }
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (tid == 256) PROF_SET(3);
 
         // ===== epilogue: TMEM -> registers -> ReLU -> Y rows of every pixel of the tile =====
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        if (tid == 256) PROF_SET(4);
         const int half = sel;                                    // two warps per lane quarter: even / odd 16-column chunks
         const int64_t ne = nbase + q * 32 + lane;
         for (int t = 0; t < T; t++) {
-            const int32_t *__restrict__ rg = tile_rows + (tile * T + t) * (int64_t)geo.G;
+            const int32_t *rg = s_rows + t * 256;
             for (int c0 = half * 16; c0 < Gp; c0 += 32) {
                 uint32_t r[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Gp + c0);
@@ -282,14 +310,14 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                             if (c0 + j < geo.G) {
                                 float y = __uint_as_float(r[j]);
                                 if (RELU) y = fmaxf(y, 0.0f);
-                                Y[(int64_t)__ldg(rg + c0 + j) * ldy + ne] = y;
+                                Y[(int64_t)rg[c0 + j] * ldy + ne] = y;
                             }
                         }
                     } else {
                         int32_t yrow[16];
                         unsigned pmask[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) yrow[j] = (c0 + j < geo.G) ? __ldg(rg + c0 + j) : -1;
+                        for (int j = 0; j < 16; j++) yrow[j] = (c0 + j < geo.G) ? rg[c0 + j] : -1;
 #pragma unroll
                         for (int j = 0; j < 16; j++) pmask[j] = (yrow[j] >= 0) ? kn_peer_mask(peers, yrow[j]) : 0u;
 #pragma unroll
@@ -310,8 +338,10 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
     }
 
+    if (tid == 256) PROF_SET(5);
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) PROF_SET(6);
     if (warp == 7) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base));
@@ -357,6 +387,16 @@ int tile_super_tiles() {
 }
 }  // namespace
 
+#ifdef KN_TILE_PROF
+KN_API int kn_debug_tile_prof(int64_t *out_host, int32_t reset) {
+    long long t[64];
+    if (reset) { memset(t, 0, sizeof(t)); KN_CUDA(cudaMemcpyToSymbol(g_tile_prof, t, sizeof(t))); return KN_OK; }
+    KN_CUDA(cudaMemcpyFromSymbol(t, g_tile_prof, sizeof(t)));
+    for (int i = 0; i < 64; i++) out_host[i] = (int64_t)t[i];
+    return KN_OK;
+}
+#endif
+
 KN_API int kn_conv2d_tiles_index(const kn_conv2d_desc *desc, const int32_t *tile_origin, int64_t n_tiles, int32_t th, int32_t tw,
                                  const int32_t *row_of_src, const int32_t *col_map, int32_t *tile_cols, int32_t *tile_rows, void *stream) {
     KN_REQUIRE(desc && desc->C > 0 && desc->M > 0 && desc->stride > 0 && (desc->P % 2) == 1 && (desc->Q % 2) == 1, "conv_tiles: bad descriptor");
@@ -391,7 +431,7 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     KN_REQUIRE(g.a0 <= 512 && g.n_a >= 2, "spmm_tile_tc: accumulators of %d pixels x %d rows leave no room for the activation ring", g.T, g.Gp);
     g.plane_bytes = g.Gp * KS * 4;
     g.slab_bytes = 2 * g.plane_bytes;
-    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * kMaxPos * 4 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
+    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * 256 * 4 + (size_t)kMaxT * kMaxPos * 4 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
     const int64_t avail = 226 * 1024 - (int64_t)fixed;
     // shared memory: the weight slabs of at least one channel chunk (+1 so the next chunk can start loading), the rest split
     // between the raw gather ring (bytes in flight towards this SM) and more weight slabs
@@ -401,7 +441,7 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     int n_slots = (int)((avail - (int64_t)n_raw * kRawStageBytes) / g.slab_bytes);
     if (n_slots > 3 * g.n_taps) n_slots = 3 * g.n_taps;
     KN_REQUIRE(n_slots >= g.n_taps + 1, "spmm_tile_tc: the weight slabs of one channel chunk do not fit shared memory (Gp=%d taps=%d)", g.Gp, g.n_taps);
-    KN_REQUIRE((size_t)(2 * n_slots + 2 * g.n_a + 2) * 8 <= 1024, "spmm_tile_tc: too many barriers");
+    KN_REQUIRE((size_t)(2 * n_slots + 2 * g.n_a + 2 * n_raw + 2) * 8 <= 1024, "spmm_tile_tc: too many barriers");
     g.n_slots = n_slots;
     g.n_raw = n_raw;
     const size_t smem = (size_t)n_slots * g.slab_bytes + (size_t)n_raw * kRawStageBytes + fixed;

@@ -1449,7 +1449,7 @@ def _conv_tiles(desc, geom, wq, bq, pix_np, row_of_src, col_map, bias_col, dev):
     if Uo % th != 0 or Vo % tw != 0 or uh * uw > 32 or th * tw * Gp + 4 * 32 > 512:
         return None
     slab = 2 * Gp * 64
-    if (226 * 1024 - (uh * uw * C * 4 + 4096) - (P * Q + 1) * slab) // 8192 < 3:
+    if (226 * 1024 - (uh * uw * C * 4 + 8192) - (P * Q + 1) * slab) // 8192 < 3:
         return None                                   # weight slabs of a channel chunk + a raw gather ring must fit shared memory
     (py, px) = (pix_np // Vo, pix_np % Vo)
     origin = (py // th * th) * Vo + (px // tw * tw)
