@@ -162,7 +162,13 @@ keyed_conv_fill_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const
     const int K_src = d.C * d.U * d.V;
     const int CPQ = d.C * d.P * d.Q;
 
-    for (int64_t g = BIG ? 0 : blockIdx.x; g < n_groups; g += BIG ? n_groups : gridDim.x) {
+    // pixels are dealt out in CONTIGUOUS blocks: the rows of one output channel for consecutive pixels are consecutive rows of
+    // the CSR, so every warp's output stream stays inside a few pages (pixel-interleaved CTAs touched 2 * M far-apart pages per
+    // pixel -- rows of different channels lie hundreds of MB apart -- and ran at 0.4 TB/s, bound by address translation)
+    const int64_t per_cta = BIG ? n_groups : (n_groups + gridDim.x - 1) / gridDim.x;
+    const int64_t g_begin = BIG ? 0 : (int64_t)blockIdx.x * per_cta;
+    const int64_t g_end = BIG ? n_groups : (g_begin + per_cta < n_groups ? g_begin + per_cta : n_groups);
+    for (int64_t g = g_begin; g < g_end; g++) {
         const int px = pix ? pix[g] : (int)g;
         const PixGeom geo = pix_geom(d, px);
         const int K_main = d.C * geo.np * geo.nq;
@@ -369,7 +375,7 @@ KN_API int kn_keyed_conv2d_fill(const kn_conv2d_desc *desc, const float *weight,
     KN_ONCE_PER_DEVICE {
         KN_CUDA(cudaFuncSetAttribute(keyed_conv_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4 * 3));
     }
-    keyed_conv_fill_kernel<false><<<grid_for(n_groups > 0 ? n_groups : 1, 1, 2), kThreads, smem, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
+    keyed_conv_fill_kernel<false><<<grid_for(n_groups > 0 ? n_groups : 1, 1, col_scale ? 2 : 3), kThreads, smem, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
                                                                                                 out_indptr, out_indices, out_data, nullptr, 0, 0);
     KN_CHECK_LAUNCH();
     return KN_OK;
