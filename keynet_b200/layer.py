@@ -38,7 +38,8 @@ class KeyedLayer(nn.Module):
         self._fused_relu = False
         self._rows = rows
         self._build_groups = bool(build_groups)
-        want_csr = bool(keep_csr) or tileshape is not None or not build_groups
+        want_csr = bool(keep_csr) or not build_groups        # tiled layers without a CSR take their tile tables from a one-channel twin
+        (self._A, self._Ainv) = (A, Ainv)
         assert A is None or isinstance(A, (MonomialKey, SparseKey)), 'A must be a key (MonomialKey / SparseKey)'
         assert isinstance(Ainv, (MonomialKey, SparseKey)), 'Ainv must be a key (MonomialKey / SparseKey)'
         t0 = time.time()
@@ -130,8 +131,9 @@ class KeyedLayer(nn.Module):
             self.W.optimize()          # pattern-grouped execution format for batched forward (no-op if the builder made it)
         if tileshape is not None:
             from .tiled import tile_keyed_layer
-            self.W = tile_keyed_layer(self.W, module, inshape, outshape, tileshape)
-        if not keep_csr and getattr(self.W, '_pg', None) is not None:
+            self.W = tile_keyed_layer(self.W, module, inshape, outshape, tileshape, self._A, self._Ainv)
+        (self._A, self._Ainv) = (None, None)              # keys are not kept with the layer
+        if not keep_csr and getattr(self.W, '_pg', None) is not None and self.W._data is not None:
             self.W.drop_csr()
             torch.cuda.empty_cache()
         if verbose():

@@ -594,12 +594,14 @@ def PermutationKeynet(inshape, net, do_output_encryption=False):
     return Keynet(inshape, net, global_geometric='permutation', do_output_encryption=do_output_encryption)
 
 
-def TiledIdentityKeynet(inshape, net, tilesize):
-    return Keynet(inshape, net, tileshape=(tilesize, tilesize))
+def TiledIdentityKeynet(inshape, net, tilesize, keep_csr=True):
+    """keep_csr=False (not in the reference): VGG16-scale networks -- conv / linear layers exist only as pattern groups and
+    the tiled views come from one-channel twins (tiled.Conv2dTiledMatrix.from_twin), never from a 120 GB expansion."""
+    return Keynet(inshape, net, tileshape=(tilesize, tilesize), keep_csr=keep_csr)
 
 
-def TiledPermutationKeynet(inshape, net, tilesize):
-    return Keynet(inshape, net, local_geometric='permutation', tileshape=(tilesize, tilesize), blocksize=tilesize)
+def TiledPermutationKeynet(inshape, net, tilesize, keep_csr=True):
+    return Keynet(inshape, net, local_geometric='permutation', tileshape=(tilesize, tilesize), blocksize=tilesize, keep_csr=keep_csr)
 
 
 def TiledOrthogonalKeynet(inshape, net, tilesize, hierarchical_permute_at_level=(0, 1)):

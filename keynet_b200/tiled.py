@@ -191,6 +191,7 @@ class Conv2dTiledMatrix(TiledMatrix):
         key = (kt * h + (si[present] % h)) * w + (sj[present] % w)
         key = torch.cat([key, torch.arange(t00['n_tiles'], device=key.device) * h * w])   # every tile owns a (0,0) entry
         n_entries = int(torch.unique(key).numel())
+        self._n_spatial_entries = n_entries
         self._n_tile_entries = n_entries
         self._nnz_tiled = n_entries * Cout * Cin
         blocks = [(int(i), int(j), int(k)) for (i, j, k) in zip(t00['block_i0'].tolist(), t00['block_j0'].tolist(), t00['block_tile'].tolist())]
@@ -203,6 +204,63 @@ class Conv2dTiledMatrix(TiledMatrix):
             blocks += [(int(i), K, int(n_entries + k)) for (i, k) in zip(tb['block_i0'].tolist(), tb['block_tile'].tolist())]   # k_offset = len(tile dict), sparse.py:769
         self._blocks = sorted(blocks, key=lambda x: (x[0], x[1]))
         self._tab = dict(n_tiles=t00['n_tiles'])
+
+    @classmethod
+    def from_twin(cls, Wexec, module, inshape, outshape, tileshape, A, Ainv):
+        """The same tiled view WITHOUT the expanded matrix (VGG16: 120 GB as CSR).  The reference takes the spatial tile
+        structure from the channel-(0,0) block of the keyed matrix (sparse.py:740,752) and assumes channel-repeated keys;
+        that block is the keyed Toeplitz matrix of a ONE-channel twin of the layer (first channel block of A and Ainv), a
+        (Hout*Wout+1) x (Hin*Win+1) matrix built by the same compiler.  Every tile entry of the twin stands for a dense
+        Cout x Cin block; the bias column is tiled from the bias vector.  Wexec: the layer's execution form (pattern
+        groups, no CSR).  Equal to Conv2dTiledMatrix(expanded matrix) wherever that fits (tests/test_gpu_tiled_vgg.py)."""
+        from . import sparse as _sp
+        (Cin, Hin, Win) = [int(v) for v in inshape]
+        (Cout, Hout, Wout) = [int(v) for v in outshape]
+        (HoWo, HiWi) = (Hout * Wout, Hin * Win)
+        (h, w) = (int(tileshape[0]), int(tileshape[1]))
+
+        def first_channel(K, n):
+            if K is None:
+                return None
+            assert isinstance(K, MonomialKey) and K.bias is None, 'tiled layers at this scale need permutation / gain keys'
+            p = K.perm[:n]
+            assert int(p.max()) < n, 'the key mixes channels: it is not tile-repeated (sparse.py:690-717 assumes it is)'
+            return MonomialKey(np.concatenate([p, [n]]), np.concatenate([K.scale[:n], np.ones(1, dtype=np.float32)]))
+        stride = module.stride[0]
+        w00 = module.weight.detach().cpu().numpy()[0:1, 0:1]
+        b0 = module.bias.detach().cpu().numpy()[0:1] if module.bias is not None else np.zeros(1, dtype=np.float32)
+        T00 = _sp.keyed_toeplitz_conv2d((1, Hin, Win), w00, b0, stride, first_channel(A, HoWo), first_channel(Ainv, HiWi), build_groups=False)
+        twin = cls(T00, (1, Hin, Win), (1, Hout, Wout), (h, w), bias=True, sanitycheck=False)
+        self = cls.__new__(cls)
+        SparseMatrix.__init__(self)
+        (self.shape, self._pg) = (Wexec.shape, Wexec._pg)
+        (self._nnz, self._device) = (Wexec.nnz(), Wexec._device if Wexec._data is None else Wexec._data.device)
+        (self._inshape, self._outshape, self._tileshape) = (inshape, outshape, (h, w))
+        (R, K) = (Cout * HoWo, Cin * HiWi)
+        assert self.shape[0] in (R + 1,) and R % h == 0 and K % w == 0
+        n_entries = twin._n_spatial_entries
+        (self._n_spatial_entries, self._n_tile_entries, self._nnz_tiled) = (n_entries, n_entries, n_entries * Cout * Cin)
+        blocks = [b for b in twin._blocks if b[1] < HiWi]                       # spatial blocks of the (0,0) block
+        # bias column: value of row r = bias of its source channel (gains applied), last row = 1
+        dev = self._device
+        bias = module.bias.detach().cpu().numpy().astype(np.float32) if module.bias is not None else np.zeros(Cout, dtype=np.float32)
+        src = np.arange(R) if A is None else A.perm[:R]
+        v = _sp._offset_round(bias, np.min(bias))[src // HoWo]
+        if A is not None:
+            v = (A.scale[:R] * v).astype(np.float32)
+        v = np.concatenate([v, np.ones(1, dtype=np.float32)])
+        nz = np.nonzero(v)[0]
+        rb = torch.from_numpy(nz.astype(np.int64)).to(dev)
+        tb = _tile_tables(rb, torch.zeros_like(rb), torch.from_numpy(v[nz]).to(dev), (R + 1, 1), (h, 1))
+        self._n_tile_entries += int(tb['tile_nnz'].sum().item())
+        self._nnz_tiled += int(tb['tile_nnz'].sum().item())
+        blocks += [(int(i), K, int(n_entries + k)) for (i, k) in zip(tb['block_i0'].tolist(), tb['block_tile'].tolist())]
+        self._blocks = sorted(blocks, key=lambda x: (x[0], x[1]))
+        self._tab = dict(n_tiles=twin._tab['n_tiles'])
+        return self
+
+    def expanded_nnz(self):
+        return int(self._nnz) if self._data is None else SparseMatrix.nnz(self)
 
     def __repr__(self):
         return str('<keynet_b200.Conv2dTiledMatrix: H=%d, W=%d, tileshape=%s, tile entries=%d>' % (*self.shape, str(self.tileshape()), self._n_tile_entries))
@@ -217,9 +275,12 @@ class Conv2dTiledMatrix(TiledMatrix):
         return int(self._nnz_tiled)
 
 
-def tile_keyed_layer(W, module, inshape, outshape, tileshape):
-    """What KeyedLayer does with tileshape (keynet/layer.py:38-41,62-65): conv -> Conv2dTiledMatrix, avgpool -> TiledMatrix."""
+def tile_keyed_layer(W, module, inshape, outshape, tileshape, A=None, Ainv=None):
+    """What KeyedLayer does with tileshape (keynet/layer.py:38-41,62-65): conv -> Conv2dTiledMatrix, avgpool -> TiledMatrix.
+    A conv layer that was built as pattern groups only (no CSR: VGG16 scale) takes its tile tables from the one-channel twin."""
     from torch import nn
+    if isinstance(module, nn.Conv2d) and W._data is None:
+        return Conv2dTiledMatrix.from_twin(W, module, inshape, outshape, tileshape, A, Ainv)
     if W._pg is None:
         W.optimize()
     if isinstance(module, nn.Conv2d):
