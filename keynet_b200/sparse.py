@@ -695,8 +695,15 @@ class SparseMatrix(object):
         x = x.to(dev, non_blocking=True) if on_host else x
         if not x.is_contiguous():
             x = x.contiguous()
-        y = spmm(self, x, relu=relu)
+        N = x.shape[1]
+        if self._data is not None and (self._pg is None or N < 32 or N % 4 != 0):
+            # plain CSR product: the dispatcher-visible op (keynet_b200/ops.py -> kn_spmm_csr_f32)
+            from . import ops as _ops       # registers the torch.library ops on first use
+            y = torch.ops.keynet_b200.spmm_csr(self._indptr, self._indices, self._data, self.shape[1], x, bool(relu))    # row pointers are absolute: views work
+        else:
+            y = spmm(self, x, relu=relu)
         return y.cpu() if on_host else y
+
 
     def dot(self, x_numpy):
         if isinstance(x_numpy, MonomialKey):

@@ -445,7 +445,36 @@ def g_tiled():
     save('tiled_kat.npz', d)
 
 
-ALL = dict(toeplitz=g_toeplitz, keygen=g_keygen, blockpermute=g_blockpermute, lenet_cfg1=g_lenet_cfg1, lenet_cfg3=g_lenet_cfg3,
+def g_params():
+    """Rows of the paper's parameter-count table (demo/figures.py:236-293) produced by the unmodified reference: numpy-seeded
+    weights (seed 0), np.random.seed(0) before every factory call.  LeNet: every row; AllConvNet: identity / permutation /
+    TiledPermutationKeynet-8 (the other rows take the reference minutes each)."""
+    import keynet.mnist, keynet.cifar10, keynet.system
+    keynet.globals.verbose(False)
+    rows = []
+
+    def keyed(f, *a, **k):
+        np.random.seed(0)
+        (sensor, knet) = f(*a, **k)
+        return int(knet.num_parameters())
+    net = numpy_weights(keynet.mnist.LeNet_AvgPool(), 0).eval()
+    inshape = (1, 28, 28)
+    rows.append(['lenet', int(keynet.torch.count_parameters(net))])
+    rows.append(['IdentityKeynet (lenet)', keyed(keynet.system.IdentityKeynet, inshape, net)])
+    rows.append(['PermutationKeynet (lenet)', keyed(keynet.system.PermutationKeynet, inshape, net)])
+    for k in (2, 4, 8):
+        rows.append(['TiledPermutationKeynet-%d (lenet)' % k, keyed(keynet.system.TiledPermutationKeynet, inshape, net, k)])
+    net = numpy_weights(keynet.cifar10.AllConvNet(batchnorm=False), 0).eval()
+    inshape = (3, 32, 32)
+    rows.append(['allconvnet', int(keynet.torch.count_parameters(net))])
+    rows.append(['IdentityKeynet (allconvnet)', keyed(keynet.system.IdentityKeynet, inshape, net)])
+    rows.append(['PermutationKeynet (allconvnet)', keyed(keynet.system.PermutationKeynet, inshape, net)])
+    rows.append(['TiledPermutationKeynet-8 (allconvnet)', keyed(keynet.system.TiledPermutationKeynet, inshape, net, 8)])
+    with open(os.path.join(HERE, 'params_kat.json'), 'w') as f:
+        json.dump(rows, f, indent=1)
+
+
+ALL = dict(params=g_params, toeplitz=g_toeplitz, keygen=g_keygen, blockpermute=g_blockpermute, lenet_cfg1=g_lenet_cfg1, lenet_cfg3=g_lenet_cfg3,
            challenge=g_challenge, lenet_givens=g_lenet_givens, acn_cfg2=g_acn_cfg2, vggtwin=g_vggtwin, tiled=g_tiled)
 
 if __name__ == '__main__':
