@@ -16,8 +16,9 @@ def count_parameters(net):
     return int(sum(p.numel() for p in net.parameters() if p.requires_grad))
 
 
-def parameter_table(which=('lenet', 'allconvnet'), seed=0, orthogonal=False, tiles=None, verbose=True):
-    """-> list of (label, count) in the order demo/figures.py prints them.  which: any of 'lenet', 'allconvnet', 'vgg16'."""
+def parameter_table(which=('lenet', 'allconvnet'), seed=0, orthogonal=False, tiles=None, verbose=True, init=None):
+    """-> list of (label, count) in the order demo/figures.py prints them.  which: any of 'lenet', 'allconvnet', 'vgg16';
+    tiles: tile sizes (default: the reference's per network); init: optional callable(net) -> net setting the weights."""
     rows = []
 
     def add(label, n):
@@ -37,7 +38,8 @@ def parameter_table(which=('lenet', 'allconvnet'), seed=0, orthogonal=False, til
     for w in which:
         (label, inshape, make, ks, small) = spec[w]
         ks = ks if tiles is None else list(tiles)
-        net = make().eval()
+        net = make()
+        net = (init(net) if init is not None else net).eval()
         add(label, count_parameters(net))
         big = {} if small else {'keep_csr': False}
         add('IdentityKeynet (%s)' % label, keyed(system.Keynet, inshape, net, **big))
