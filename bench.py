@@ -743,7 +743,7 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
         check = {'plain_net': check_against_plain_net(wl, x, y[:, :-1], n=4)}
     nnz_local = m.num_parameters_local()
     (ms, ms_e2e, nnz_max, mem_max) = _reduce_max([ms, ms_e2e, float(nnz_local), torch.cuda.max_memory_allocated() / 1e9], world)
-    s = torch.tensor([float(nnz_local)], device='cuda', dtype=torch.float64)
+    s = torch.tensor([float(nnz_local), float(m.h2d_bytes(tuple(host_in[0].shape)))], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     if rank != 0:
@@ -764,9 +764,11 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
                       'nnz': int(nnz), 'nnz_max_rank': int(nnz_max), 'key_compile_s': round(t_compile, 3), 'hbm_allocated_gb_max_rank': round(mem_max, 2),
                       'all_gather_bytes_per_step': int(gather), 'peer_store_fraction': m.peer_store_fraction() if m.fused else None,
                       'rank0_layer_ms_spmm_barrier': [(names[k], a, b) for (k, a, b) in layer_ms], 'rank0_barrier_ms_per_step': round(sum(b for (_, _, b) in layer_ms), 3),
+                      'layer_sync': ('neighbourhood flags (kn_peer_sync): a rank waits only for the ranks it reads from / will store to' if (m.fused and m.selective and m.flag_sync) else 'barrier over all ranks') if m.fused else 'NCCL all-gather',
+                      'sync_timed_out': bool(m.sync_timed_out()) if m.fused else None,
                       'check': check, 'l2': 'inputs larger than L2'},
-           'e2e': {'value': N * K / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(host_in[0].numel() * 4) * world, 'd2h_bytes_per_step': int(host_out[0].numel() * 4) * world,
-                   'note': 'ShardedKeyedModel.forward_host_many on every rank: pinned H2D of the (replicated) batch, sensor encryption, sharded chain, D2H of the logits; the H2D of step k+1 overlaps step k',
+           'e2e': {'value': N * K / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(float(s[1])), 'd2h_bytes_per_step': int(host_out[0].numel() * 4) * world,
+                   'note': 'ShardedKeyedModel.forward_host_many on every rank: pinned H2D of the image rows the rank\'s first layer reads (its band + halo; all ranks together: h2d_bytes_per_step), sensor encryption, sharded chain, D2H of the logits on every rank; the H2D of step k+1 overlaps step k',
                    'ms_per_step': ms_e2e / K},
            'gpu_launches': (sum(L.W._pg.launches() if L.W._pg is not None else 1 for L in m.layers) + 2 * len(m.layers) + 2) * K, 'clocks': clocks,
            'roofline': {'bound': 'tensor', 'kernel': 'whole sharded network (pg_tc_kernel tcgen05 3xTF32 is > 90 % of the step)', 'achieved': tflops, 'peak': tpeak * world, 'unit': 'TFLOP/s',

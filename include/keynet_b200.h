@@ -64,6 +64,14 @@ typedef struct kn_peers {
     const uint8_t *row_mask;    /* device memory or NULL */
 } kn_peers;
 
+/* Neighbourhood synchronisation between the layers of the fused row-sharded forward: flags_host[i] = device address on rank
+ * i of an int32[8] flag array in NVLink-mapped memory.  The calling rank stores `epoch` into flags[q][my_rank] of every rank q
+ * in signal_mask (after a system-scope fence: its earlier peer stores are visible first) and then waits until
+ * flags[my_rank][p] >= epoch for every rank p in wait_mask.  Replaces a barrier over all ranks: a conv layer sharded by
+ * pixels only depends on its two neighbours.  timeout_flag (device int, nullable) is set if a peer never arrives. */
+int kn_peer_sync(const uint64_t *flags_host, int32_t world, int32_t my_rank, uint32_t signal_mask, uint32_t wait_mask, int32_t epoch,
+                 int32_t *timeout_flag, void *stream);
+
 /* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------
  * Replaces SparseMatrix.torchdot (keynet/sparse.py:488-492 -> scipy csr_matvecs), called from
  * KeyedLayer.forward / .decrypt (keynet/layer.py:92,99) and KeyedSensor.encrypt (system.py:254).

@@ -14,7 +14,7 @@ KN_ERR_UNSUPPORTED = -3
 
 # every symbol include/keynet_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    'kn_abi_version', 'kn_last_error', 'kn_device_info',
+    'kn_abi_version', 'kn_last_error', 'kn_device_info', 'kn_peer_sync',
     'kn_spmm_csr_f32', 'kn_spmm_csr_rows_f32', 'kn_exclusive_scan_i64',
     'kn_csr_row_pattern_hash', 'kn_pg_verify', 'kn_pg_pack', 'kn_spmm_pg_f32', 'kn_spmm_cg_f32',
     'kn_pg_tc_split', 'kn_pg_tc_tensormaps', 'kn_spmm_pg_tc_f32', 'kn_debug_tc_timing',
@@ -84,6 +84,7 @@ def lib():
     L.kn_device_info.restype = i32
     L.kn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_int64)]
     sig = {
+        'kn_peer_sync': [vp, ctypes.c_int32, ctypes.c_int32, u32, u32, ctypes.c_int32, vp, vp],
         'kn_spmm_csr_f32': [vp, vp, vp, i64, i64, vp, i64, vp, i64, i64, u32, pp, vp],
         'kn_spmm_csr_rows_f32': [vp, vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u32, pp, vp],
         'kn_csr_row_pattern_hash': [vp, vp, i64, vp, vp],

@@ -65,6 +65,28 @@ def peer_row_masks(need, rank, chunk, n_mine):
     return mask
 
 
+def sync_sets(reads_k, reads_next, rank):
+    """Neighbourhood synchronisation after layer k (fused row-sharded forward).  reads_k[q, p] = rank q reads rows that rank p
+    produced in layer k; reads_next the same for layer k+1 (None after the last layer).  Returns (signal_mask, wait_mask):
+    this rank waits for the ranks whose layer-k rows it reads (RAW) and for the ranks it will store rows to in layer k+1 --
+    layer k+1 on this rank overwrites, on those ranks, the ping-pong buffer their layer k is still reading (WAR) -- and it
+    signals every rank that waits for it.  With shards cut by image rows both sets are the two spatial neighbours."""
+    reads_k = np.asarray(reads_k, dtype=bool)
+    world = reads_k.shape[0]
+
+    def waits(r):
+        w = reads_k[r].copy()
+        if reads_next is not None:
+            w |= np.asarray(reads_next, dtype=bool)[:, r]
+        w[r] = False
+        return w
+    wait = waits(rank)
+    signal = np.array([waits(q)[rank] for q in range(world)], dtype=bool)
+    signal[rank] = False
+    to_mask = lambda v: int(sum(1 << i for i in range(world) if v[i]))
+    return (to_mask(signal), to_mask(wait))
+
+
 class LayerShard(object):
     """Bookkeeping of one row-sharded layer: which canonical rows this rank computes and where every canonical row
     lives in the gathered buffer [world*chunk + 1] (last position = homogeneous coordinate)."""
@@ -116,6 +138,7 @@ class ShardedKeyedModel(object):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.fused = bool(fused)
         self.selective = bool(selective)       # fused only: store a row only to the peers whose next layer reads it
+        self.flag_sync = True                  # selective only: neighbourhood flags (kn_peer_sync) instead of a barrier over all ranks per layer
         self._symm = {}
         f_keypair = system.keypair_policy(**keynet_kwargs)
         self.sensor = system.KeyedSensor(inshape, f_keypair('input', inshape))
@@ -133,6 +156,7 @@ class ShardedKeyedModel(object):
             import torch.distributed as dist
             group = self.group if self.group is not None else dist.group.WORLD
             masks = []
+            reads = []                      # reads[k][q, p]: rank q reads rows of layer k produced by rank p
             for (k, L) in enumerate(self.layers):
                 sh = L._shard
                 n_mine = len(sh.my_rows)
@@ -141,11 +165,16 @@ class ShardedKeyedModel(object):
                     assert need.numel() == sh.n_phys
                     allneed = torch.empty((self.world, sh.n_phys), dtype=torch.uint8, device=dev)
                     dist.all_gather_into_tensor(allneed, need.reshape(1, -1).contiguous(), group=group)
-                    m = peer_row_masks(allneed.cpu().numpy() != 0, self.rank, sh.chunk, n_mine)
+                    an = allneed.cpu().numpy() != 0
+                    m = peer_row_masks(an, self.rank, sh.chunk, n_mine)
+                    slots = an[:, :self.world * sh.chunk].reshape(self.world, self.world, sh.chunk)
+                    reads.append(slots.any(axis=2))
                 else:
                     m = np.full(n_mine, (1 << self.world) - 1, dtype=np.uint8)      # the logits go to everyone
+                    reads.append(np.ones((self.world, self.world), dtype=bool))
                 masks.append(torch.from_numpy(m).to(dev))
             self._masks = masks
+            self._sync = [sync_sets(reads[k], reads[k + 1] if k + 1 < len(reads) else None, self.rank) for k in range(len(reads))]
         return self._masks
 
     def peer_store_fraction(self):
@@ -201,11 +230,37 @@ class ShardedKeyedModel(object):
                 spmm(L.W, X, relu=relu, out=Yfull[self.rank * sh.chunk:self.rank * sh.chunk + n_mine], peers=peers)
             Yfull[-1].fill_(1.0)                                        # homogeneous coordinate: local
             self._stamp()
-            h.barrier()                                                 # every rank's stores have landed everywhere
+            if self.selective and self.flag_sync:
+                self._peer_sync(k, dev)                                 # signal the ranks that read these rows, wait for the ranks read from
+            else:
+                h.barrier()                                             # every rank's stores have landed everywhere
             X = Yfull
         self._stamp()
         self._parity = (parity + len(self.layers)) % 2
         return X
+
+    def _peer_sync(self, k, dev):
+        """Neighbourhood synchronisation after layer k (kn_peer_sync): flags in symmetric memory, one epoch per call."""
+        from . import _native
+        import ctypes
+        if getattr(self, '_flags', None) is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            t = symm_mem.empty((16,), dtype=torch.int32, device=dev)
+            t.zero_()
+            h = symm_mem.rendezvous(t, group)
+            h.barrier()                                                 # every rank's flags are zero before anyone signals
+            self._flags = (t, h, (ctypes.c_uint64 * 8)(*[int(p) for p in h.buffer_ptrs]))
+            self._epoch = 0
+            self._sync_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        (signal, wait) = self._sync[k]
+        self._epoch += 1
+        _native.check(_native.lib().kn_peer_sync(self._flags[2], self.world, self.rank, signal, wait, self._epoch, _native.ptr(self._sync_timeout), _native.stream_ptr()))
+
+    def sync_timed_out(self):
+        """True if a peer failed to arrive at some neighbourhood synchronisation (checked by tests / the bench after a run)."""
+        return getattr(self, '_sync_timeout', None) is not None and bool(self._sync_timeout.item() != 0)
 
     def _stamp(self):
         if self.time_layers:
@@ -277,13 +332,20 @@ class ShardedKeyedModel(object):
         for b in range(2):
             st['free'][b].record(main)
 
+        band = self._input_band()
+
         def h2d(k):
             b = k % 2
             with torch.cuda.stream(st['stream']):
                 st['stream'].wait_event(st['free'][b])
                 if st['stage'][b] is None or st['stage'][b].shape != batches[k].shape:
-                    st['stage'][b] = torch.empty(batches[k].shape, dtype=torch.float32, device=dev)
-                st['stage'][b].copy_(batches[k], non_blocking=True)
+                    st['stage'][b] = torch.zeros(batches[k].shape, dtype=torch.float32, device=dev)
+                if band is None or batches[k].ndim != 4:
+                    st['stage'][b].copy_(batches[k], non_blocking=True)
+                else:
+                    # only the image rows this rank's first layer reads (its band of output pixels + halo) cross PCIe
+                    (y0, y1) = band
+                    st['stage'][b][:, :, y0:y1, :].copy_(batches[k][:, :, y0:y1, :], non_blocking=True)
                 st['done'][b].record(st['stream'])
         if len(batches) > 0:
             h2d(0)
@@ -307,6 +369,32 @@ class ShardedKeyedModel(object):
         if nbad != 0:
             raise ValueError('invalid affine vector: %d outputs lost the homogeneous coordinate' % nbad)
         return outs
+
+    def _input_band(self):
+        """Image rows [y0, y1) whose pixels this rank's first keyed layer reads (through the image key), or None when it reads
+        (nearly) everything.  The sensor output rows outside the band are never read by this rank's shard."""
+        if not hasattr(self, '_band'):
+            self._band = None
+            (A, _) = self.sensor.keypair()
+            (C, H, W) = [int(v) for v in self.sensor._inshape[1:]]
+            if self.world > 1 and hasattr(A, 'perm') and getattr(A, 'bias', None) is None and len(self.layers) > 0:
+                used = self.layers[0].W.used_columns().cpu().numpy()
+                rows = np.nonzero(used[:C * H * W])[0]                     # keyed rows read (the homogeneous row is local)
+                if len(rows) > 0:
+                    d = np.asarray(A.perm)[rows]                            # raw pixel behind every keyed row
+                    y = (d % (H * W)) // W
+                    (y0, y1) = (int(y.min()), int(y.max()) + 1)
+                    if (y1 - y0) < 0.75 * H:
+                        self._band = (y0, y1)
+        return self._band
+
+    def h2d_bytes(self, batch_shape):
+        """Bytes forward_host_many copies to this rank's GPU for one host batch of this shape."""
+        band = self._input_band()
+        n = int(np.prod(batch_shape))
+        if band is None or len(batch_shape) != 4:
+            return 4 * n
+        return 4 * n * (band[1] - band[0]) // int(batch_shape[2])
 
     def forward(self, x_cipher):
         from . import torch as ktorch

@@ -289,7 +289,7 @@ def load_shard(path, rank, world, group=None, optimize=True):
     assert (int(s['rank']), int(s['world'])) == (int(rank), int(world)), 'shard file belongs to rank %d of %d' % (s['rank'], s['world'])
     m = _dist.ShardedKeyedModel.__new__(_dist.ShardedKeyedModel)
     (m.rank, m.world, m.group, m.fused, m.selective) = (int(rank), int(world), group, bool(s['fused']), bool(s['selective']))
-    (m._symm, m._masks, m.time_layers, m._events) = ({}, None, False, [])
+    (m._symm, m._masks, m.time_layers, m._events, m.flag_sync) = ({}, None, False, [], True)
     m.sensor = _system.KeyedSensor(tuple(s['inshape']), (_key_load(s['sensor']['A']), _key_load(s['sensor']['Ainv'])))
     m._outshape = tuple(s['outshape'])
     layers = []

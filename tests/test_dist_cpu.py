@@ -170,3 +170,35 @@ def test_shard_plan_properties():
                         last = px.max()
                     assert len(s.my_rows) % outshape[0] == 0
                     assert all(np.sum(px == p) == outshape[0] for p in np.unique(px))
+
+
+def test_sync_sets_neighbourhood_and_war():
+    """kn_peer_sync plan: a rank waits for the ranks it reads from (RAW) and for the ranks it will store to in the next layer
+    (WAR on the ping-pong buffer), and signals exactly the ranks that wait for it."""
+    from keynet_b200.dist import sync_sets
+    W = 4
+    line = np.zeros((W, W), dtype=bool)
+    for r in range(W):
+        for q in (r - 1, r, r + 1):
+            if 0 <= q < W:
+                line[r, q] = True                          # conv layer cut by image rows: a rank reads itself and its neighbours
+    everyone = np.ones((W, W), dtype=bool)
+    for r in range(W):
+        (sig, wait) = sync_sets(line, line, r)
+        nb = sum(1 << q for q in (r - 1, r + 1) if 0 <= q < W)
+        assert sig == nb and wait == nb
+    # next layer dense (fc6 reads everything): every rank will store to every rank -> waits for all (WAR), signals all
+    for r in range(W):
+        (sig, wait) = sync_sets(line, everyone, r)
+        assert wait == ((1 << W) - 1) & ~(1 << r) and sig == wait
+    # last layer: everyone reads the logits
+    (sig, wait) = sync_sets(everyone, None, 2)
+    assert sig == wait == 0b1011
+    # consistency: q is in r's wait set  <=>  r is in q's signal set
+    rs = np.random.RandomState(0)
+    (a, b) = (rs.rand(W, W) < 0.4, rs.rand(W, W) < 0.4)
+    sets = [sync_sets(a, b, r) for r in range(W)]
+    for r in range(W):
+        for q in range(W):
+            if r != q:
+                assert bool((sets[r][1] >> q) & 1) == bool((sets[q][0] >> r) & 1)

@@ -52,7 +52,8 @@ def _worker(rank, world, port, q, fused=False, selective=True):
             dist.barrier()
         y = m.forward(xc).reshape(64, -1).cpu().numpy()
         y = m.forward(xc).reshape(64, -1).cpu().numpy()       # twice: ping-pong buffers are reused
-        q.put((rank, bool(np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)), float(np.abs(y - y_ref).max()), m.num_parameters_local(), m.peer_store_fraction()))
+        ok = bool(np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)) and not m.sync_timed_out()
+        q.put((rank, ok, float(np.abs(y - y_ref).max()), m.num_parameters_local(), m.peer_store_fraction()))
     finally:
         dist.destroy_process_group()
 
