@@ -244,6 +244,197 @@ keyed_conv_fill_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const
     }
 }
 
+// ---- fill, row-order variant ------------------------------------------------------------------------------------------------
+// The per-pixel kernel above writes the M rows of a pixel, which lie M * Uo*Vo rows apart in the CSR: its 2*M output streams
+// per CTA jump between pages hundreds of MB apart (~1 TB/s).  Here the rows are written IN ROW ORDER -- one warp per row,
+// consecutive warps on consecutive rows, one sequential output stream per array for the whole layer -- and the sorted
+// (column, tap) list of the row's pixel comes from a table:
+//   * a column map (permuted input key): kn lists kernel = the per-pixel sort above, run once per pixel into a scratch buffer
+//     [pixel][K] that stays L2-resident while the M channel rows of the layer pass over it;
+//   * no column map (identity input key: every conv that follows a keyed ReLU): column = pixel base + relative column of the
+//     tap, so ONE list per border class (which taps are in bounds: <= 9 classes for a 3x3 kernel) serves every pixel.
+// The bias entry (homogeneous column: always the largest column) is appended by the row kernel.
+__global__ void __launch_bounds__(kThreads)
+keyed_conv_lists_kernel(kn_conv2d_desc d, const int32_t *__restrict__ pix, int64_t n_groups, const int32_t *__restrict__ col_map,
+                        const float *__restrict__ col_scale, int K2, int2 *__restrict__ lists, float *__restrict__ list_scale)
+{
+    extern __shared__ int32_t smem[];
+    int32_t *s_key = smem;
+    int32_t *s_tap = smem + kSortCap;
+    __shared__ int s_unsorted;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int px = pix ? pix[g] : (int)g;
+        const PixGeom geo = pix_geom(d, px);
+        const int K = d.C * geo.np * geo.nq;
+        if (threadIdx.x == 0) s_unsorted = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < K; e += kThreads) {
+            int32_t cs, wi;
+            tap_of(d, geo, e, cs, wi);
+            s_key[e] = col_map ? __ldg(col_map + cs) : cs;
+            s_tap[e] = e;
+        }
+        __syncthreads();
+        int unsorted = 0;
+        for (int e = threadIdx.x + 1; e < K; e += kThreads) unsorted |= (s_key[e - 1] > s_key[e]) ? 1 : 0;
+        if (unsorted) s_unsorted = 1;
+        __syncthreads();
+        if (s_unsorted) bitonic_sort_kp(s_key, s_tap, K);
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += kThreads) {
+            int32_t cs, wi;
+            tap_of(d, geo, s_tap[i], cs, wi);
+            lists[g * (int64_t)K2 + i] = make_int2(s_key[i], wi);
+            if (list_scale) list_scale[g * (int64_t)K2 + i] = __ldg(col_scale + cs);
+        }
+        __syncthreads();
+    }
+}
+
+// lists of the border classes (identity input key): class (p0, np, q0, nq) = which taps are in bounds; entries are
+// (column relative to the pixel's base column u*V + v, weight offset), ascending by construction.  Class index =
+// ((p0+ph)*P + np-1) * Q*Q + (q0+qh)*Q + nq-1.
+__device__ __forceinline__ int class_index(const kn_conv2d_desc &d, const PixGeom &g) {
+    return (((g.p0 + (d.P - 1) / 2) * d.P + (g.np - 1)) * d.Q + (g.q0 + (d.Q - 1) / 2)) * d.Q + (g.nq - 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv_class_lists_kernel(kn_conv2d_desc d, int K2, int2 *__restrict__ lists)
+{
+    const int ph = (d.P - 1) / 2, qh = (d.Q - 1) / 2;
+    const int cls = blockIdx.x;
+    const int inq = cls % d.Q, iq0 = (cls / d.Q) % d.Q, inp = (cls / (d.Q * d.Q)) % d.P, ip0 = cls / (d.Q * d.Q * d.P);
+    const int p0 = ip0 - ph, np = inp + 1, q0 = iq0 - qh, nq = inq + 1;
+    if (p0 + np - 1 > ph || q0 + nq - 1 > qh) return;            // not a window of the kernel
+    const int taps = np * nq, K = d.C * taps;
+    for (int e = threadIdx.x; e < K; e += kThreads) {
+        const int c = e / taps, t = e - c * taps;
+        const int ip = t / nq, iq = t - ip * nq;
+        const int p = p0 + ip, q = q0 + iq;
+        lists[cls * (int64_t)K2 + e] = make_int2(c * d.U * d.V + p * d.V + q, (c * d.P + (p + ph)) * d.Q + (q + qh));
+    }
+}
+
+// zero weights among the in-bounds taps of every (output channel, border class): with permutation-only keys the stored entries
+// of a row are its taps minus these (the exact zeros scipy's SpGEMM drops), so the count pass needs no per-entry work
+__global__ void __launch_bounds__(kThreads)
+conv_class_zeros_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const float *__restrict__ bias, int n_cls, int32_t *__restrict__ zeros)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ph = (d.P - 1) / 2, qh = (d.Q - 1) / 2;
+    const int CPQ = d.C * d.P * d.Q;
+    for (int64_t i = (int64_t)blockIdx.x * kWarps + warp; i < (int64_t)d.M * n_cls; i += (int64_t)gridDim.x * kWarps) {
+        const int m = (int)(i / n_cls), cls = (int)(i - (int64_t)m * n_cls);
+        const int inq = cls % d.Q, iq0 = (cls / d.Q) % d.Q, inp = (cls / (d.Q * d.Q)) % d.P, ip0 = cls / (d.Q * d.Q * d.P);
+        const int p0 = ip0 - ph, np = inp + 1, q0 = iq0 - qh, nq = inq + 1;
+        int cnt = 0;
+        if (p0 + np - 1 <= ph && q0 + nq - 1 <= qh) {
+            const int taps = np * nq, K = d.C * taps;
+            for (int e = lane; e < K; e += 32) {
+                const int c = e / taps, t = e - c * taps;
+                const int ip = t / nq, iq = t - ip * nq;
+                cnt += (__ldg(weight + (int64_t)m * CPQ + (c * d.P + (p0 + ip + ph)) * d.Q + (q0 + iq + qh)) == 0.0f) ? 1 : 0;
+            }
+            if (lane == 0 && d.has_bias) cnt += (__ldg(bias + m) == 0.0f) ? 1 : 0;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) zeros[i] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+keyed_conv_count_class_kernel(kn_conv2d_desc d, const int32_t *__restrict__ pix, int64_t n_groups, const int32_t *__restrict__ row_of_src,
+                              int n_cls, const int32_t *__restrict__ zeros, int keep_zeros, int64_t *__restrict__ row_nnz)
+{
+    const int UoVo = (d.U / d.stride) * (d.V / d.stride);
+    const int64_t n_items = (int64_t)d.M * n_groups;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(it / n_groups);
+        const int64_t g = it - (int64_t)m * n_groups;
+        const int px = pix ? pix[g] : (int)g;
+        const int64_t s = (int64_t)m * UoVo + px;
+        const int64_t r = row_of_src ? row_of_src[s] : s;
+        if (r < 0) continue;
+        const PixGeom geo = pix_geom(d, px);
+        const int K = d.C * geo.np * geo.nq + (d.has_bias ? 1 : 0);
+        row_nnz[r] = K - (keep_zeros ? 0 : zeros[(int64_t)m * n_cls + class_index(d, geo)]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t R_src = (int64_t)d.M * UoVo;
+        const int64_t r = row_of_src ? row_of_src[R_src] : R_src;
+        if (r >= 0) row_nnz[r] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+keyed_conv_rows_kernel(kn_conv2d_desc d, const float *__restrict__ weight, const float *__restrict__ bias,
+                       const int32_t *__restrict__ pix, int64_t n_groups, const int32_t *__restrict__ row_of_src,
+                       const float *__restrict__ row_scale, int keep_zeros,
+                       const int2 *__restrict__ lists, const float *__restrict__ list_scale, int class_mode,
+                       const int32_t *__restrict__ col_map, const float *__restrict__ col_scale, int K2,
+                       const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices, float *__restrict__ out_data)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int UoVo = (d.U / d.stride) * (d.V / d.stride);
+    const int64_t R_src = (int64_t)d.M * UoVo;
+    const int CPQ = d.C * d.P * d.Q;
+    const int K_src = d.C * d.U * d.V;
+    const int32_t key_last = col_map ? __ldg(col_map + K_src) : K_src;          // homogeneous column: always the largest
+    const float scale_last = col_scale ? __ldg(col_scale + K_src) : 1.0f;
+    const int has_col_scale = col_scale != nullptr;
+    const int64_t n_items = (int64_t)d.M * n_groups;
+    // consecutive warps take consecutive rows (channel-major, pixels of the list in order): sequential output streams
+    for (int64_t it = (int64_t)blockIdx.x * kWarps + warp; it < n_items; it += (int64_t)gridDim.x * kWarps) {
+        const int m = (int)(it / n_groups);
+        const int64_t g = it - (int64_t)m * n_groups;
+        const int px = pix ? pix[g] : (int)g;
+        const int64_t s = (int64_t)m * UoVo + px;
+        const int64_t r = row_of_src ? row_of_src[s] : s;
+        if (r < 0) continue;
+        const PixGeom geo = pix_geom(d, px);
+        const int K = d.C * geo.np * geo.nq;
+        const int64_t lg = class_mode ? class_index(d, geo) : g;
+        const int2 *__restrict__ lst = lists + lg * (int64_t)K2;
+        const float *__restrict__ lsc = list_scale ? list_scale + lg * (int64_t)K2 : nullptr;
+        const int32_t kb = class_mode ? geo.u * d.V + geo.v : 0;
+        const float a = row_scale ? row_scale[r] : 1.0f;
+        const float *__restrict__ wm = weight + (int64_t)m * CPQ;
+        int64_t out = out_indptr[r];
+#pragma unroll 4
+        for (int i0 = 0; i0 < K; i0 += 32) {
+            const int i = i0 + lane;
+            float v = 0.0f;
+            bool keep = false;
+            int32_t key = 0;
+            if (i < K) {
+                const int2 e = lst[i];
+                key = e.x + kb;
+                v = keyed(__ldg(wm + e.y), a, lsc ? lsc[i] : 1.0f, row_scale != nullptr, has_col_scale != 0);
+                keep = keep_zeros || v != 0.0f;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int64_t pos = out + __popc(mask & ((1u << lane) - 1u));
+                out_indices[pos] = key;
+                out_data[pos] = v;
+            }
+            out += __popc(mask);
+        }
+        if (d.has_bias && lane == 0) {
+            const float v = keyed(__ldg(bias + m), a, scale_last, row_scale != nullptr, has_col_scale != 0);
+            if (keep_zeros || v != 0.0f) { out_indices[out] = key_last; out_data[out] = v; }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {               // homogeneous row e_last
+        const int64_t r = row_of_src ? row_of_src[R_src] : R_src;
+        if (r >= 0 && out_indptr[r + 1] > out_indptr[r]) {
+            out_indices[out_indptr[r]] = key_last;
+            out_data[out_indptr[r]] = keyed(1.0f, row_scale ? row_scale[r] : 1.0f, scale_last, row_scale != nullptr, has_col_scale != 0);
+        }
+    }
+}
+
 // ---- pattern groups straight from the geometry -------------------------------------------------------------------------
 // rows[g][M] (compiled row of every output channel of pixel g), cols[g][K_pad] (new column of every tap, Toeplitz order,
 // padding repeats the first column), group_k[g]
@@ -342,7 +533,20 @@ KN_API int kn_keyed_conv2d_count(const kn_conv2d_desc *desc, const float *weight
     KN_REQUIRE(n_groups >= 0, "keyed_conv: negative group count");
     KN_REQUIRE(weight && row_nnz, "keyed_conv: null pointer");
     KN_REQUIRE(!desc->has_bias || bias, "keyed_conv: has_bias set but bias is null");
-    keyed_conv_count_kernel<<<grid_for(n_groups * desc->M, kWarps, 16), kThreads, 0, (cudaStream_t)stream>>>(*desc, weight, bias, pix, n_groups, row_of_src, row_scale, col_scale, keep_zeros, row_nnz);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!row_scale && !col_scale && n_groups > 64) {
+        // permutation-only keys: a row stores its taps minus the zero weights among them, a function of (channel, border class)
+        const int n_cls = desc->P * desc->P * desc->Q * desc->Q;
+        int32_t *zeros = nullptr;
+        KN_CUDA(cudaMallocAsync((void **)&zeros, sizeof(int32_t) * (size_t)desc->M * n_cls, s));
+        conv_class_zeros_kernel<<<grid_for((int64_t)desc->M * n_cls, kWarps, 16), kThreads, 0, s>>>(*desc, weight, bias, n_cls, zeros);
+        keyed_conv_count_class_kernel<<<grid_for((int64_t)desc->M * n_groups, kThreads, 16), kThreads, 0, s>>>(*desc, pix, n_groups, row_of_src, n_cls, zeros, keep_zeros, row_nnz);
+        const cudaError_t e = cudaGetLastError();
+        KN_CUDA(cudaFreeAsync(zeros, s));
+        if (e != cudaSuccess) { kn_set_error("keyed_conv: launch failed: %s", cudaGetErrorString(e)); return KN_ERR_CUDA; }
+        return KN_OK;
+    }
+    keyed_conv_count_kernel<<<grid_for(n_groups * desc->M, kWarps, 16), kThreads, 0, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, row_scale, col_scale, keep_zeros, row_nnz);
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
@@ -371,14 +575,42 @@ KN_API int kn_keyed_conv2d_fill(const kn_conv2d_desc *desc, const float *weight,
         if (e != cudaSuccess) { kn_set_error("keyed_conv: launch failed: %s", cudaGetErrorString(e)); return KN_ERR_CUDA; }
         return KN_OK;
     }
-    const size_t smem = (size_t)kSortCap * 4 * (col_scale ? 3 : 2);
-    KN_ONCE_PER_DEVICE {
-        KN_CUDA(cudaFuncSetAttribute(keyed_conv_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4 * 3));
+    // ---- row-order path: a table of sorted (column, tap) lists + one warp per row, rows written in order
+    {
+        const int K2 = desc->C * desc->P * desc->Q;
+        const bool per_pixel = (col_map != nullptr) || (col_scale != nullptr);
+        int2 *lists = nullptr; float *list_scale = nullptr;
+        const size_t smem = (size_t)kSortCap * 4 * 2;
+        KN_ONCE_PER_DEVICE {
+            KN_CUDA(cudaFuncSetAttribute(keyed_conv_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 4 * 2));
+            // the scratch lists come from the stream-ordered pool: keep its memory between calls (the default threshold of 0
+            // returns it to the driver at every synchronisation, i.e. hundreds of MB are re-created per layer)
+            int dev = 0; cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        }
+        if (per_pixel) {
+            // permuted / scaled input key: one sorted list per pixel, L2-resident while the M channel rows pass over it
+            KN_CUDA(cudaMallocAsync((void **)&lists, (size_t)n_groups * K2 * sizeof(int2), s));
+            if (col_scale) KN_CUDA(cudaMallocAsync((void **)&list_scale, (size_t)n_groups * K2 * sizeof(float), s));
+            keyed_conv_lists_kernel<<<grid_for(n_groups, 1, 3), kThreads, smem, s>>>(*desc, pix, n_groups, col_map, col_scale, K2, lists, list_scale);
+        } else {
+            // identity input key: one list per border class
+            const int n_cls = desc->P * desc->P * desc->Q * desc->Q;
+            KN_CUDA(cudaMallocAsync((void **)&lists, (size_t)n_cls * K2 * sizeof(int2), s));
+            conv_class_lists_kernel<<<n_cls, kThreads, 0, s>>>(*desc, K2, lists);
+        }
+        keyed_conv_rows_kernel<<<grid_for((int64_t)desc->M * n_groups, kWarps, 8), kThreads, 0, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, row_scale, keep_zeros,
+                                                                                                    lists, list_scale, per_pixel ? 0 : 1, col_map, col_scale, K2,
+                                                                                                    out_indptr, out_indices, out_data);
+        const cudaError_t e = cudaGetLastError();
+        KN_CUDA(cudaFreeAsync(lists, s));
+        if (list_scale) KN_CUDA(cudaFreeAsync(list_scale, s));
+        if (e != cudaSuccess) { kn_set_error("keyed_conv: launch failed: %s", cudaGetErrorString(e)); return KN_ERR_CUDA; }
+        return KN_OK;
     }
-    keyed_conv_fill_kernel<false><<<grid_for(n_groups > 0 ? n_groups : 1, 1, col_scale ? 2 : 3), kThreads, smem, s>>>(*desc, weight, bias, pix, n_groups, row_of_src, col_map, row_scale, col_scale, keep_zeros,
-                                                                                                out_indptr, out_indices, out_data, nullptr, 0, 0);
-    KN_CHECK_LAUNCH();
-    return KN_OK;
 }
 
 KN_API int kn_conv2d_groups_index(const kn_conv2d_desc *desc, const int32_t *pix, int64_t n_groups, const int32_t *row_of_src, const int32_t *col_map,
