@@ -610,14 +610,26 @@ def bench_replicas(name, batch, K, warmup, rank, world, local_rank, want_cpu=Tru
     alg = dict(plan.algorithmic_bytes())
     flops = {nm: 2.0 * W.nnz() * N for (nm, W, _) in plan.layers}
     (dom, dom_ms) = max(per_layer, key=lambda kv: kv[1])
-    domW = [W for (nm, W, _) in plan.layers if nm == dom][0]
-    grouped = domW._pg is not None and N >= 32 and N % 4 == 0
+    names = [nm for (nm, _, _) in plan.layers]
+    dom_i = names.index(dom)
+    domW = plan.layers[dom_i][1]
+    fused_pair = dom_i in getattr(plan, 'fused', {})
+    if fused_pair:                                   # one launch computes this layer AND the pooling layer that follows
+        partner = names[dom_i + 1]
+        alg[dom] += alg[partner]
+        flops[dom] += flops[partner]
+    grouped = domW._pg is not None and N >= 32 and N % 4 == 0 and not fused_pair
     on_tc = grouped and any(c['tc'] is not None for c in domW._pg.classes) and N >= 128
+    tiled = on_tc and any(c.get('tile') is not None for c in domW._pg.classes)
     clustered = grouped and any(c.get('cg') is not None for c in domW._pg.classes)
     any_tc = any(W._pg is not None and any(c['tc'] is not None for c in W._pg.classes) for (_, W, _) in plan.layers) and N >= 128
-    kname = ('pg_tc_kernel (tcgen05 3xTF32)' if on_tc else ('pg_cluster_kernel (fp32 FMA, staged gathers)' if clustered else 'pg_simt_kernel / pg_small_kernel (fp32 FMA)')) if grouped else 'spmm_rowwarp_kernel'
-    if grouped:
+    if fused_pair:
+        kname = 'convpool_kernel (fused conv + ReLU + average pooling of layers %s + %s, intermediate in shared memory, fp32 FMA)' % (dom, partner)
+    elif grouped:
+        kname = ('pg_tile_tc_kernel (tcgen05 3xTF32, spatial tiles)' if tiled else 'pg_tc_kernel (tcgen05 3xTF32)') if on_tc else ('pg_cluster_kernel (fp32 FMA, staged gathers)' if clustered else 'pg_simt_kernel / pg_small_kernel (fp32 FMA)')
         kname += ', pattern groups (G, K_pad, n_groups)=%s' % str(domW._pg.summary()['classes'])
+    else:
+        kname = 'spmm_rowwarp_kernel'
     hbm_achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
     total_alg = sum(alg.values())
     (traffic, traffic_note) = profiled_traffic(name, N, dom)
@@ -640,7 +652,8 @@ def bench_replicas(name, batch, K, warmup, rank, world, local_rank, want_cpu=Tru
                      'network': {'algorithmic_bytes_per_step': total_alg, 'hbm_achieved_gbs': total_alg / step_s / 1e9, 'hbm_frac': total_alg / step_s / 1e9 / peak,
                                  'algorithmic_tflops': sum(flops.values()) / step_s / 1e12,
                                  'note': 'CSR-equivalent algorithmic bytes (8 B per stored entry + row pointers + activations, SURVEY 8d) / step time / measured HBM peak'},
-                     'layers_ms': {k: round(v, 4) for (k, v) in per_layer}})
+                     'layers_ms': {k: round(v, 4) for (k, v) in per_layer},
+                     'fused_pairs': ['%s+%s' % (names[i], names[i + 1]) for i in sorted(getattr(plan, 'fused', {}))]})
     nnz = int(sum(L[1].nnz() for L in plan.layers))
     rec = {'metric': 'encrypted_images_per_sec', 'value': world * N * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': warmup,
            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': '3xtf32 (f32 accumulate)' if any_tc else 'f32', 'data': 'synthetic',

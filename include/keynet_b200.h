@@ -264,6 +264,17 @@ int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, const i
                         int32_t C, int32_t G, int32_t th, int32_t tw, int32_t stride, int32_t P, int32_t Q,
                         const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, uint32_t flags, const kn_peers *peers, void *stream);
 
+/* ---- fused keyed conv (+ReLU) -> keyed average pooling for small layers (csrc/convpool.cu) ---------------------------
+ * Y = W_pool . relu(W_conv . X) for two consecutive keyed layers (keynet/layer.py:32-35 conv, :48-59 avgpool, ReLU of
+ * keynet/system.py:92) under permutation-only keys, with the intermediate (all conv outputs of an image) in shared memory
+ * instead of HBM.  weight / bias: the conv's offset-rounded coefficients; pool_w: the pooling coefficient as the reference
+ * stores it (offset-rounded 1/k^2, keynet/sparse.py:206-212; windows centred, zero padded, divisor k*k);
+ * xrow[C*U*V + 1]: activation row of every conv input (c, y, x) under the conv's input key, last = homogeneous row;
+ * yrow[M*Up*Vp + 1]: output row of every pooled (m, py, px) under the pool's output key, last = homogeneous row. */
+int kn_convpool_f32(const kn_conv2d_desc *desc, const float *weight, const float *bias, const int32_t *xrow,
+                    int32_t pool_k, int32_t pool_stride, float pool_w, const int32_t *yrow,
+                    const float *X, int64_t ldx, float *Y, int64_t ldy, int64_t n_vecs, void *stream);
+
 /* Gather rows of a CSR matrix: out row i = in row row_ids[i] (SparseMatrix key A applied on the left
  * for explicit matrices, e.g. sensor keys / ReLU keys, keynet/layer.py:46). */
 int kn_csr_gather_rows_count(const int64_t *indptr, const int64_t *row_ids, int64_t n_rows, int64_t *row_nnz, void *stream);

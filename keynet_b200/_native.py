@@ -21,7 +21,7 @@ SYMBOLS = [
     'kn_toeplitz_conv2d_count', 'kn_toeplitz_conv2d_fill', 'kn_linear_count', 'kn_linear_fill',
     'kn_keycompile_count', 'kn_keycompile_fill', 'kn_csr_gather_rows_count', 'kn_csr_gather_rows_fill',
     'kn_affine_to_linear_t', 'kn_linear_to_affine_t',
-    'kn_conv2d_tiles_index', 'kn_spmm_tile_tc_f32',
+    'kn_conv2d_tiles_index', 'kn_spmm_tile_tc_f32', 'kn_convpool_f32',
     'kn_keyed_conv2d_count', 'kn_keyed_conv2d_fill', 'kn_conv2d_groups_index', 'kn_conv2d_groups_values',
     'kn_spgemm_bound', 'kn_spgemm_rows', 'kn_csr_compact', 'kn_encrypt_monomial_t', 'kn_splitk_reduce_f32',
 ]
@@ -114,6 +114,7 @@ def lib():
         'kn_conv2d_groups_values': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, i64, vp, vp, vp, ctypes.c_int32, vp, vp],
         'kn_conv2d_tiles_index': [ctypes.POINTER(kn_conv2d_desc), vp, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp],
         'kn_spmm_tile_tc_f32': [vp, vp, vp, ctypes.c_int32, i64] + [ctypes.c_int32] * 7 + [vp, i64, vp, i64, i64, u32, pp, vp],
+        'kn_convpool_f32': [ctypes.POINTER(kn_conv2d_desc), vp, vp, vp, ctypes.c_int32, ctypes.c_int32, f32, vp, vp, i64, vp, i64, i64, vp],
         'kn_csr_gather_rows_count': [vp, vp, i64, vp, vp],
         'kn_csr_gather_rows_fill': [vp, vp, vp, vp, i64, vp, vp, vp, vp],
         'kn_affine_to_linear_t': [vp, i64, i64, vp, i64, vp],

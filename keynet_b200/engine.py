@@ -1,12 +1,58 @@
 """Batched forward engine: the keyed layer chain for a fixed batch size with pre-allocated, feature-major
 activation buffers, launched either eagerly or as one CUDA graph (the chain is launch-latency bound for
 LeNet-sized nets).  B200-side replacement for looping `KeyedLayer.forward` (keynet/system.py:130-133)."""
+import os
+
 import numpy as np
 import torch
 
 from . import _native
 from . import layer as _layer
 from .sparse import spmm
+
+
+_FUSE = [os.environ.get('KEYNET_B200_FUSE', '1') != '0']
+
+
+def fusion_enabled(flag=None):
+    """Switch for the fused conv (+ReLU) -> average-pooling kernel (csrc/convpool.cu); off = one launch per keyed layer."""
+    if flag is not None:
+        _FUSE[0] = bool(flag)
+    return _FUSE[0]
+
+
+def _fusable(Wc, relu_c, Wp, N):
+    """Tables of the fused conv -> ReLU -> avgpool kernel for two consecutive layers, or None: permutation-only keys, the
+    conv's output key cancelling against the pool's input key, and the whole image (input + conv output) of 4 batch columns
+    fitting shared memory."""
+    (rc, rp) = (getattr(Wc, '_recipe', None), getattr(Wp, '_recipe', None))
+    if rc is None or rp is None or rc['kind'] != 'conv' or rp['kind'] != 'pool' or not relu_c or N % 4 != 0:
+        return None
+    (C, U, V, M, P, Q, stride) = rc['geom']
+    (Cp, Up_in, Vp_in, _, k, _, pstride) = rp['geom']
+    (Uo, Vo) = (U // stride, V // stride)
+    if (Cp, Up_in, Vp_in) != (M, Uo, Vo) or Uo % pstride != 0 or Vo % pstride != 0:
+        return None
+    if ((C * U * V + M * Uo * Vo) * 4 + (M + 5) * (C * P * Q + 1)) * 4 > 220 * 1024:
+        return None
+    n_mid = M * Uo * Vo + 1
+    (po, pi) = (rc['out_perm'], rp['in_perm'])
+    if (po is None) != (pi is None):
+        return None
+    if po is not None and not np.array_equal(np.asarray(pi)[np.asarray(po)], np.arange(n_mid)):
+        return None                                       # the pool does not read the conv's rows where the conv writes them
+    dev = torch.device('cuda', torch.cuda.current_device())
+    n_in = C * U * V + 1
+    xrow = np.arange(n_in, dtype=np.int32) if rc['in_perm'] is None else np.asarray(rc['in_perm'], dtype=np.int32)
+    n_out = M * (Uo // pstride) * (Vo // pstride) + 1
+    if rp['out_perm'] is None:
+        yrow = np.arange(n_out, dtype=np.int32)
+    else:
+        yrow = np.empty(n_out, dtype=np.int32)
+        yrow[np.asarray(rp['out_perm'])] = np.arange(n_out, dtype=np.int32)
+    return dict(desc=_native.kn_conv2d_desc(C, U, V, M, P, Q, int(stride), 0, 1), w=torch.from_numpy(np.ascontiguousarray(rc['fq'], dtype=np.float32)).to(dev),
+                b=torch.from_numpy(np.ascontiguousarray(rc['bq'], dtype=np.float32)).to(dev), xrow=torch.from_numpy(xrow).to(dev), yrow=torch.from_numpy(yrow).to(dev),
+                k=int(k), pstride=int(pstride), pool_w=float(rp['pool_w']))
 
 
 class ForwardPlan(object):
@@ -33,7 +79,20 @@ class ForwardPlan(object):
         self.bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
         from .sparse import MonomialKey
         self.fused_encrypt = isinstance(sensor.keypair()[0], MonomialKey)          # image key applied inside the transpose kernel
-        self.launches_per_run = (1 if self.fused_encrypt else 3) + sum((W._pg.launches() if (W._pg is not None and N >= 32 and N % 4 == 0) else 1) for (_, W, _) in self.layers[1:])
+        # conv (+ReLU) -> avgpool pairs whose intermediate fits shared memory run as ONE launch (csrc/convpool.cu)
+        self.fused = {}
+        if fusion_enabled():
+            i = 1
+            while i + 1 < len(self.layers):
+                f = _fusable(self.layers[i][1], self.layers[i][2], self.layers[i + 1][1], N) if not self.layers[i + 1][2] else None
+                if f is not None:
+                    self.fused[i] = f
+                    i += 2
+                else:
+                    i += 1
+        skip = set(i + 1 for i in self.fused)
+        self.launches_per_run = (1 if self.fused_encrypt else 3) + sum(0 if i in skip else (1 if i in self.fused else (W._pg.launches() if (W._pg is not None and N >= 32 and N % 4 == 0) else 1))
+                                                                        for (i, (_, W, _)) in enumerate(self.layers) if i >= 1)
         self.time_layers = time_layers
         # per-layer CUDA events on the launch stream, one set per timed step (read back after the timed region)
         self.layer_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.layers]
@@ -48,16 +107,25 @@ class ForwardPlan(object):
         L = _native.lib()
         s = _native.stream_ptr()
         x = None
+        skip = -1
         for (i, (name, W, relu)) in enumerate(self.layers):
             if self.time_layers:
                 self.layer_events[self.event_set][i][0].record()
             if i == 0:
                 self.sensor.encrypt_into(self.images, self.acts[0])     # homogenise + transpose + image key (one kernel for monomial keys)
+            elif i == skip:
+                pass                                                    # produced by the fused launch of the previous layer
+            elif i in self.fused:
+                f = self.fused[i]
+                _native.check(L.kn_convpool_f32(f['desc'], _native.ptr(f['w']), _native.ptr(f['b']), _native.ptr(f['xrow']), f['k'], f['pstride'], f['pool_w'], _native.ptr(f['yrow']),
+                                                _native.ptr(x), self.N, _native.ptr(self.acts[i + 1]), self.N, self.N, s))
+                skip = i + 1
             else:
                 spmm(W, x, relu=relu, out=self.acts[i])
             if self.time_layers:
                 self.layer_events[self.event_set][i][1].record()
-            x = self.acts[i]
+            if i not in self.fused:
+                x = self.acts[i]
         _native.check(L.kn_linear_to_affine_t(_native.ptr(x), self.N, self.N, self.K, _native.ptr(self.logits), 1e-3, _native.ptr(self.bad), s))
 
     def _capture(self):

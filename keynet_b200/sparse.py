@@ -1481,6 +1481,18 @@ def _conv_tiles(desc, geom, wq, bq, pix_np, row_of_src, col_map, bias_col, dev):
     return dict(maps=maps, hi=hi, lo=lo, cols=tile_cols, rows=tile_rows, bias_col=bias_col, n_tiles=n_tiles, C=C, G=M, th=th, tw=tw, stride=stride, P=P, Q=Q)
 
 
+def _recipe(kind, geom, A, Ainv, rows, col_remap, **extra):
+    """How a keyed layer was built (geometry, coefficients, key permutations): lets the batched engine fuse a conv (+ReLU)
+    with the average pooling that follows it (csrc/convpool.cu).  None when the layer is sharded or its keys are not plain
+    permutations -- those layers are never fused."""
+    if rows is not None or col_remap is not None:
+        return None
+    for K in (A, Ainv):
+        if K is not None and not (isinstance(K, MonomialKey) and K.bias is None and K.is_unscaled()):
+            return None
+    return dict(kind=kind, geom=geom, out_perm=None if (A is None or A.is_unpermuted()) else A.perm, in_perm=None if Ainv.is_unpermuted() else Ainv.perm, **extra)
+
+
 def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_groups=True, col_remap=None, n_cols_phys=None, want_csr=True):
     """W_hat = A . toeplitz(conv2d) . Ainv built on the GPU for monomial keys (keynet/layer.py:32-35).
 
@@ -1493,6 +1505,7 @@ def keyed_toeplitz_conv2d(inshape, f, bias, stride, A, Ainv, rows=None, build_gr
         clustered = M <= PatternGroups.CG_MAX_G and (C * P * Q + 1 + 31) // 32 * 32 <= PatternGroups.CG_KERNEL_MAX_K
         W = _keyed_conv_direct((C, U, V, M, P, Q, int(stride), True), fq, bq, A, Ainv, rows, col_remap, n_cols_phys, want_csr, build_groups, dev, clustered=clustered)
         if W is not None:
+            W._recipe = _recipe('conv', (C, U, V, M, P, Q, int(stride)), A, Ainv, rows, col_remap, fq=fq, bq=bq)
             return W
     R = M * (U // stride) * (V // stride) + 1
     K = C * U * V + 1
@@ -1590,6 +1603,7 @@ def keyed_toeplitz_avgpool2d(inshape, kernel_size, stride, A, Ainv, rows=None, c
     csr = _toeplitz_rows(desc, wq, None, ids, n, dev)
     csr = _keycompile(csr, n, K, A, Ainv, dev, row_scale_slice=sel)
     W = SparseMatrix(((n, Kp), *csr), device=dev)
+    W._recipe = _recipe('pool', (C, U, V, C, k, k, int(stride)), A, Ainv, rows, col_remap, pool_w=float(wq.reshape(-1)[0]))
     return W
 
 
