@@ -11,11 +11,14 @@ from . import layer as _layer
 from .sparse import spmm
 
 
-_FUSE = [os.environ.get('KEYNET_B200_FUSE', '1') != '0']
+_FUSE = [os.environ.get('KEYNET_B200_FUSE', '0') != '0']
 
 
 def fusion_enabled(flag=None):
-    """Switch for the fused conv (+ReLU) -> average-pooling kernel (csrc/convpool.cu); off = one launch per keyed layer."""
+    """Switch for the fused conv (+ReLU) -> average-pooling kernel (csrc/convpool.cu); off (default) = one launch per keyed
+    layer.  Measured on B200, LeNet batch 65 536: the fused pairs take 1.16 + 1.85 ms against 0.66 + 0.81 ms unfused -- the
+    intermediate stays in shared memory (HBM traffic 5.8x lower) but with 4 batch columns per CTA the direct convolution runs at
+    15 % of the fp32 FMA peak; it needs register tiling over pixels before it pays.  KEYNET_B200_FUSE=1 enables it."""
     if flag is not None:
         _FUSE[0] = bool(flag)
     return _FUSE[0]

@@ -18,16 +18,16 @@ def test_fused_lenet_matches_unfused_and_oracle(keys, N):
     np.random.seed(2)
     (sensor, knet) = system.Keynet((1, 28, 28), net, **keys)
     x = torch.randn(N, 1, 28, 28, generator=torch.Generator().manual_seed(N)).cuda()
-    plan = engine.ForwardPlan(sensor, knet, N, use_graph=False)
+    try:
+        engine.fusion_enabled(True)
+        plan = engine.ForwardPlan(sensor, knet, N, use_graph=False)
+    finally:
+        engine.fusion_enabled(False)
     assert sorted(plan.fused) == [1, 3]                      # conv1+pool1, conv2+pool2
     y = plan.run_device(x).clone()
-    try:
-        engine.fusion_enabled(False)
-        plain = engine.ForwardPlan(sensor, knet, N, use_graph=False)
-        assert plain.fused == {}
-        y0 = plain.run_device(x).clone()
-    finally:
-        engine.fusion_enabled(True)
+    plain = engine.ForwardPlan(sensor, knet, N, use_graph=False)
+    assert plain.fused == {}
+    y0 = plain.run_device(x).clone()
     assert torch.allclose(y, y0, rtol=1e-4, atol=1e-6 * float(y0.abs().max()) + 1e-7)
     layers = bench.oracle_layers_from_gpu(sensor, knet)
     ref = ko.linear_to_affine(ko.keyed_forward(layers, ko.affine_to_linear(x.cpu().numpy()), threads=4))
@@ -42,4 +42,8 @@ def test_gain_keys_are_not_fused():
     net = nets.LeNet_AvgPool().eval()
     np.random.seed(2)
     (sensor, knet) = system.Keynet((1, 28, 28), net, global_geometric='permutation', global_photometric='uniform_random_gain', beta=1.0)
-    assert engine.ForwardPlan(sensor, knet, 64, use_graph=False).fused == {}
+    try:
+        engine.fusion_enabled(True)
+        assert engine.ForwardPlan(sensor, knet, 64, use_graph=False).fused == {}
+    finally:
+        engine.fusion_enabled(False)
