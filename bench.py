@@ -401,7 +401,7 @@ def time_oracle(layers, inshape, n_images, threads, repeats=1):
 def cpu_baseline(layers, inshape, budget_s=15.0):
     threads = host_threads()
     t_probe = time_oracle(layers, inshape, 32, threads)
-    n = int(max(32, min(16384, (budget_s / max(t_probe / 32.0, 1e-6)))))
+    n = int(max(32, min(262144, (budget_s / max(t_probe / 32.0, 1e-6)))))
     dt = time_oracle(layers, inshape, n, threads)
     return {'value': n / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
             'sample': '%d images through the same compiled layer stack, oracle csr_matvecs port (OpenMP over rows), %.1f s' % (n, dt)}
