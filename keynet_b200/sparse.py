@@ -1359,8 +1359,9 @@ def _keyed_conv_direct(geom, wq, bq, A, Ainv, rows, col_remap, n_cols_phys, want
     row_scale = None
     if A is not None and not A.is_unscaled():
         row_scale = torch.from_numpy(np.ascontiguousarray(A.scale[sel])).to(dev)
-    w = torch.from_numpy(np.ascontiguousarray(wq, dtype=np.float32)).to(dev)
-    b = torch.from_numpy(np.ascontiguousarray(bq, dtype=np.float32)).to(dev) if has_bias else None
+    as_dev = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous() if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(dev)
+    w = as_dev(wq)                                       # (a device tensor is used as is: no host round trip for a 411 MB fc6)
+    b = as_dev(bq) if has_bias else None
     # ---- canonical CSR (or only its row counts: nnz() of a layer that never holds a CSR)
     indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     check(L.kn_keyed_conv2d_count(desc, ptr(w), ptr(b), ptr(pix), n_groups, ptr(row_of_src), ptr(row_scale), ptr(col_scale), 0, ptr(indptr[1:]), stream_ptr()))
@@ -1636,8 +1637,8 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
     (n_out, n_in) = W.shape
     if _DIRECT[0] and (A is None or isinstance(A, MonomialKey)) and isinstance(Ainv, MonomialKey) and Ainv.bias is None and (A is None or A.bias is None):
         # a linear layer is a 1x1 convolution on a 1x1 image: one output "pixel", one pattern group holding every row
-        wn = W.cpu().numpy()
-        bn = None if bias is None else torch.as_tensor(bias).detach().cpu().numpy().astype(np.float32)
+        wn = W                                                  # stays on the device
+        bn = None if bias is None else torch.as_tensor(bias).detach().to(device=dev, dtype=torch.float32).contiguous()
         (A_, rows_, n_out_) = (A, rows, int(n_out))
         if rows is not None:
             # a row shard of a linear layer is a smaller linear layer: its weight rows in the shard's own order, the output
@@ -1647,8 +1648,9 @@ def keyed_linear(weight, bias, A, Ainv, rows=None, col_remap=None, n_cols_phys=N
             src_ = sel_ if A is None else A.perm[sel_]
             main_ = src_ < n_out
             n_out_ = int(main_.sum())
-            wn = np.ascontiguousarray(wn[src_[main_]])
-            bn = None if bn is None else np.ascontiguousarray(bn[src_[main_]])
+            take = torch.from_numpy(np.ascontiguousarray(src_[main_])).to(dev)
+            wn = W[take].contiguous()
+            bn = None if bn is None else bn[take].contiguous()
             rows_ = np.where(main_, np.cumsum(main_) - 1, n_out_).astype(np.int64)          # local row -> row of the reduced layer
             scale_ = np.ones(n_out_ + 1, dtype=np.float32)
             if A is not None:
