@@ -704,6 +704,18 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
         return m.forward_linear(Xenc.t())
 
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    for _ in range(2):
+        y = step()
+    graphed = False
+    if fused and world > 1 and N >= 32 and N % 4 == 0 and os.environ.get('KEYNET_B200_SHARD_GRAPH', '1') != '0':
+        # the whole sharded chain (SpMM launches, peer stores, neighbourhood syncs) as CUDA graphs: at 8 GPUs a layer is shorter
+        # than the host work that launches it
+        m.capture(N)
+        graphed = True
+
+        def step():
+            m.sensor.encrypt_into(x.reshape(N, D), m._gx)
+            return m.forward_graph(m._gx)
     for _ in range(warmup):
         y = step()
     _barrier(world)
@@ -716,6 +728,7 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
     e1.record()
     _barrier(world)
     ms = e0.elapsed_time(e1)
+    y = y.clone()
     # ---- end to end: pinned host batch in, logits out, on every rank (the batch is replicated: every rank encrypts it)
     host_in = [torch.randn((N,) + wl['inshape']).pin_memory() for _ in range(2)]
     Kout = int(y.shape[1]) - 1
@@ -748,7 +761,8 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
             clocks['note'] = 'timed region shorter than the sampling period: %d more identical (untimed) steps were run while sampling' % int(extra.item())
     # one extra (untimed) forward with per-layer events
     m.time_layers = True
-    y = step()
+    m.sensor.encrypt_into(x.reshape(N, D), Xenc)
+    y = m.forward_linear(Xenc.t())                      # eager: per-layer events cannot be recorded inside a graph replay
     layer_ms = [(k, round(a, 3), round(b, 3)) for (k, a, b) in m.layer_times_ms()]
     m.time_layers = False
     check = None
@@ -778,7 +792,7 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
                       'all_gather_bytes_per_step': int(gather), 'peer_store_fraction': m.peer_store_fraction() if m.fused else None,
                       'rank0_layer_ms_spmm_barrier': [(names[k], a, b) for (k, a, b) in layer_ms], 'rank0_barrier_ms_per_step': round(sum(b for (_, _, b) in layer_ms), 3),
                       'layer_sync': ('neighbourhood flags (kn_peer_sync): a rank waits only for the ranks it reads from / will store to' if (m.fused and m.selective and m.flag_sync) else 'barrier over all ranks') if m.fused else 'NCCL all-gather',
-                      'sync_timed_out': bool(m.sync_timed_out()) if m.fused else None,
+                      'sync_timed_out': bool(m.sync_timed_out()) if m.fused else None, 'cuda_graph': graphed,
                       'check': check, 'l2': 'inputs larger than L2'},
            'e2e': {'value': N * K / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': int(float(s[1])), 'd2h_bytes_per_step': int(host_out[0].numel() * 4) * world,
                    'note': 'ShardedKeyedModel.forward_host_many on every rank: pinned H2D of the image rows the rank\'s first layer reads (its band + halo; all ranks together: h2d_bytes_per_step), sensor encryption, sharded chain, D2H of the logits on every rank; the H2D of step k+1 overlaps step k',

@@ -65,11 +65,12 @@ typedef struct kn_peers {
 } kn_peers;
 
 /* Neighbourhood synchronisation between the layers of the fused row-sharded forward: flags_host[i] = device address on rank
- * i of an int32[8] flag array in NVLink-mapped memory.  The calling rank stores `epoch` into flags[q][my_rank] of every rank q
- * in signal_mask (after a system-scope fence: its earlier peer stores are visible first) and then waits until
- * flags[my_rank][p] >= epoch for every rank p in wait_mask.  Replaces a barrier over all ranks: a conv layer sharded by
+ * i of an int32[8] flag array in NVLink-mapped memory.  epoch_counter: device int32 of the calling rank, advanced by one per
+ * call (all ranks make the same sequence of calls; keeping the epoch on the device makes the launch replayable in a CUDA
+ * graph).  The calling rank stores the new epoch into flags[q][my_rank] of every rank q in signal_mask (after a system-scope
+ * fence: its earlier peer stores are visible first) and then waits until flags[my_rank][p] >= epoch for every p in wait_mask.  Replaces a barrier over all ranks: a conv layer sharded by
  * pixels only depends on its two neighbours.  timeout_flag (device int, nullable) is set if a peer never arrives. */
-int kn_peer_sync(const uint64_t *flags_host, int32_t world, int32_t my_rank, uint32_t signal_mask, uint32_t wait_mask, int32_t epoch,
+int kn_peer_sync(const uint64_t *flags_host, int32_t world, int32_t my_rank, uint32_t signal_mask, uint32_t wait_mask, int32_t *epoch_counter,
                  int32_t *timeout_flag, void *stream);
 
 /* ---- SpMM:  Y[n_rows][n_vecs] = W . X  (+ optional ReLU) --------------------------------

@@ -84,7 +84,7 @@ def lib():
     L.kn_device_info.restype = i32
     L.kn_device_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_int64)]
     sig = {
-        'kn_peer_sync': [vp, ctypes.c_int32, ctypes.c_int32, u32, u32, ctypes.c_int32, vp, vp],
+        'kn_peer_sync': [vp, ctypes.c_int32, ctypes.c_int32, u32, u32, vp, vp, vp],
         'kn_spmm_csr_f32': [vp, vp, vp, i64, i64, vp, i64, vp, i64, i64, u32, pp, vp],
         'kn_spmm_csr_rows_f32': [vp, vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u32, pp, vp],
         'kn_csr_row_pattern_hash': [vp, vp, i64, vp, vp],

@@ -64,14 +64,20 @@ KnPeersScope::~KnPeersScope() { g_peers = saved; }
 // WAITS only for the ranks it depends on (its spatial neighbours for conv / pool layers), instead of a barrier over all ranks:
 // flags[r][p] (int32, one array per rank in NVLink-mapped memory) holds the last epoch rank p signalled to rank r.
 namespace {
-struct KnSyncArgs { int32_t *flags[8]; int world, me; unsigned signal_mask, wait_mask; int epoch; int *timeout_flag; };
+struct KnSyncArgs { int32_t *flags[8]; int world, me; unsigned signal_mask, wait_mask; int32_t *epoch_counter; int *timeout_flag; };
 
 __global__ void peer_sync_kernel(const __grid_constant__ KnSyncArgs a) {
     const int t = threadIdx.x;
+    // the epoch lives in device memory and advances by one per call: every rank makes the same sequence of calls, so the
+    // counters agree, and a CUDA graph that captured this launch can be replayed (an epoch passed by value would repeat)
+    __shared__ int s_epoch;
+    if (t == 0) { s_epoch = *a.epoch_counter + 1; *a.epoch_counter = s_epoch; }
+    __syncthreads();
+    const int epoch = s_epoch;
     __threadfence_system();                       // the preceding kernels' peer stores are performed before the flags are
     if (t < a.world && ((a.signal_mask >> t) & 1u)) {
         int32_t *dst = a.flags[t] + a.me;
-        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(dst), "r"(a.epoch) : "memory");
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(dst), "r"(epoch) : "memory");
     }
     if (t < a.world && ((a.wait_mask >> t) & 1u)) {
         const int32_t *src = a.flags[a.me] + t;
@@ -79,22 +85,23 @@ __global__ void peer_sync_kernel(const __grid_constant__ KnSyncArgs a) {
         long long spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if (v >= a.epoch) break;
+            if (v >= epoch) break;
             __nanosleep(64);
         } while (++spins < (1ll << 24));          // ~seconds: a peer that never arrives must not hang the GPU
-        if (v < a.epoch && a.timeout_flag) atomicExch(a.timeout_flag, 1);
+        if (v < epoch && a.timeout_flag) atomicExch(a.timeout_flag, 1);
     }
     __syncthreads();
     __threadfence_system();
 }
 }  // namespace
 
-KN_API int kn_peer_sync(const uint64_t *flags_host, int32_t world, int32_t my_rank, uint32_t signal_mask, uint32_t wait_mask, int32_t epoch,
+KN_API int kn_peer_sync(const uint64_t *flags_host, int32_t world, int32_t my_rank, uint32_t signal_mask, uint32_t wait_mask, int32_t *epoch_counter,
                         int32_t *timeout_flag, void *stream) {
+    KN_REQUIRE(epoch_counter != nullptr, "peer_sync: null epoch counter");
     KN_REQUIRE(flags_host != nullptr && world >= 1 && world <= 8 && my_rank >= 0 && my_rank < world, "peer_sync: bad arguments (world=%d rank=%d)", world, my_rank);
     KnSyncArgs a;
     for (int i = 0; i < 8; i++) a.flags[i] = (i < world) ? reinterpret_cast<int32_t *>(flags_host[i]) : nullptr;
-    a.world = world; a.me = my_rank; a.signal_mask = signal_mask & ~(1u << my_rank); a.wait_mask = wait_mask & ~(1u << my_rank); a.epoch = epoch;
+    a.world = world; a.me = my_rank; a.signal_mask = signal_mask & ~(1u << my_rank); a.wait_mask = wait_mask & ~(1u << my_rank); a.epoch_counter = epoch_counter;
     a.timeout_flag = timeout_flag;
     peer_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     KN_CHECK_LAUNCH();

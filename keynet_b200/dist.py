@@ -252,11 +252,10 @@ class ShardedKeyedModel(object):
             h = symm_mem.rendezvous(t, group)
             h.barrier()                                                 # every rank's flags are zero before anyone signals
             self._flags = (t, h, (ctypes.c_uint64 * 8)(*[int(p) for p in h.buffer_ptrs]))
-            self._epoch = 0
+            self._epoch = torch.zeros(1, dtype=torch.int32, device=dev)      # advanced on the device by every kn_peer_sync
             self._sync_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
         (signal, wait) = self._sync[k]
-        self._epoch += 1
-        _native.check(_native.lib().kn_peer_sync(self._flags[2], self.world, self.rank, signal, wait, self._epoch, _native.ptr(self._sync_timeout), _native.stream_ptr()))
+        _native.check(_native.lib().kn_peer_sync(self._flags[2], self.world, self.rank, signal, wait, _native.ptr(self._epoch), _native.ptr(self._sync_timeout), _native.stream_ptr()))
 
     def sync_timed_out(self):
         """True if a peer failed to arrive at some neighbourhood synchronisation (checked by tests / the bench after a run)."""
@@ -314,6 +313,42 @@ class ShardedKeyedModel(object):
         # last layer: undo the shard-major order (a gather of K+1 rows)
         return X[self._out_positions(dev)].t().contiguous()
 
+    def capture(self, N):
+        """Capture the fused forward for batches of N (a multiple of 4, at least 32) into CUDA graphs -- one per ping-pong parity --
+        after it has run eagerly at least once (symmetric buffers, flags, split-K scratch exist).  At 8 GPUs a VGG16 layer
+        takes 50-500 us of GPU time, less than the Python + ctypes work to launch it: replaying a graph removes those gaps.
+        forward_graph(X) then copies X [D+1, N] into the static input and replays."""
+        assert self.fused and self.selective and self.flag_sync and N >= 32 and N % 4 == 0
+        dev = torch.device('cuda', torch.cuda.current_device())
+        D1 = self.layers[0].W.shape[1]
+        self._gx = torch.zeros((D1, N), dtype=torch.float32, device=dev)
+        self._graphs = {}
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        saved = getattr(self, '_parity', 0)
+        with torch.cuda.stream(side):
+            for parity in (0, 1):
+                self._parity = parity
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    y = self.forward_linear(self._gx.t())
+                self._graphs[parity] = (g, y)
+        torch.cuda.current_stream().wait_stream(side)
+        self._parity = saved
+        self._graph_N = N
+        return self
+
+    def forward_graph(self, X):
+        """X: encrypted batch, feature-major [D+1, N] on this device (the sensor's encrypt_into layout).  Returns N x (K+1)."""
+        parity = getattr(self, '_parity', 0)
+        (g, y) = self._graphs[parity]
+        if X.data_ptr() != self._gx.data_ptr():
+            self._gx.copy_(X, non_blocking=True)
+        g.replay()
+        self._parity = (parity + len(self.layers)) % 2
+        return y
+
     def _out_positions(self, dev):
         if getattr(self, '_pos', None) is None:
             self._pos = torch.from_numpy(self.layers[-1]._shard.position).to(dev)
@@ -357,10 +392,11 @@ class ShardedKeyedModel(object):
             main.wait_event(st['done'][b])
             x = st['stage'][b]
             (N, D) = (int(x.shape[0]), int(np.prod(x.shape[1:])))
-            X = torch.empty((D + 1, N), dtype=torch.float32, device=dev)
+            graphed = getattr(self, '_graphs', None) is not None and self._graph_N == N
+            X = self._gx if graphed else torch.empty((D + 1, N), dtype=torch.float32, device=dev)
             self.sensor.encrypt_into(x.reshape(N, D), X)
             st['free'][b].record(main)
-            y = self.forward_linear(X.t())                              # [N, K+1]; .t() of a transposed view is free
+            y = self.forward_graph(X) if graphed else self.forward_linear(X.t())      # [N, K+1]; .t() of a transposed view is free
             K = y.shape[1] - 1
             logits = torch.empty((N, K), dtype=torch.float32, device=dev)
             _native.check(_native.lib().kn_linear_to_affine_t(_native.ptr(y.t().contiguous()), N, N, K, _native.ptr(logits), 1e-3, _native.ptr(bad), _native.stream_ptr()))

@@ -53,6 +53,13 @@ def _worker(rank, world, port, q, fused=False, selective=True):
         y = m.forward(xc).reshape(64, -1).cpu().numpy()
         y = m.forward(xc).reshape(64, -1).cpu().numpy()       # twice: ping-pong buffers are reused
         ok = bool(np.allclose(y, y_ref, rtol=1e-4, atol=1e-5)) and not m.sync_timed_out()
+        if fused and selective:                                # the same chain replayed as CUDA graphs (one per ping-pong parity)
+            m.capture(64)
+            X = xc.cuda().t().contiguous()
+            for _ in range(3):
+                yg = m.forward_graph(X)[:, :-1].cpu().numpy()
+                ok = ok and bool(np.allclose(yg, y_ref, rtol=1e-4, atol=1e-5))
+            ok = ok and not m.sync_timed_out()
         q.put((rank, ok, float(np.abs(y - y_ref).max()), m.num_parameters_local(), m.peer_store_fraction()))
     finally:
         dist.destroy_process_group()
