@@ -707,7 +707,7 @@ def bench_rows(name, batch, K, warmup, rank, world, local_rank, fused=True, want
     for _ in range(2):
         y = step()
     graphed = False
-    if fused and world > 1 and N >= 32 and N % 4 == 0 and os.environ.get('KEYNET_B200_SHARD_GRAPH', '1') != '0':
+    if fused and m.selective and m.flag_sync and world > 1 and N >= 32 and N % 4 == 0 and os.environ.get('KEYNET_B200_SHARD_GRAPH', '1') != '0':
         # the whole sharded chain (SpMM launches, peer stores, neighbourhood syncs) as CUDA graphs: at 8 GPUs a layer is shorter
         # than the host work that launches it
         m.capture(N)

@@ -105,7 +105,7 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
 
     if (warp == 0) {
         // ===== TMA producer: weight block planes (hi, lo), 16 k x Gp rows per stage =====
-        if (lane == 0) {
+        if (elect_one()) {
             const int grow = (int)((block_of ? (int64_t)__ldg(block_of + g) : g) * G) + row0;      // rows of the group's unique value block
             int s = 0; uint32_t ph = 0;                          // ring position / phase kept incrementally (no runtime div/mod)
             for (int ks = 0; ks < n_ksteps; ks++) {
@@ -125,11 +125,8 @@ pg_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__
             }
         }
     } else if (warp == 1 || (warp == 3 && NB == 2)) {
-        // ===== MMA issuers: one elected thread per batch tile =====
-        // A single thread issues one tcgen05.mma per ~117 cycles whatever its shape (measured, scratch/umma_rate.cu),
-        // while a tf32 128 x 96 x 8 MMA occupies the tensor pipe for only 48 cycles: one issuer per accumulator
-        // (warp 1 -> batch tile 0, warp 3 -> batch tile 1) keeps the pipe fed for N < 256.
-        if (lane == 0) {
+        // ===== MMA issuers: one elected thread per batch tile (warp 1 -> batch tile 0, warp 3 -> batch tile 1) =====
+        if (elect_one()) {
             const int b = (warp == 1) ? 0 : 1;
             const uint32_t idesc = make_idesc(BM, Gp);
             const uint32_t idesc2 = make_idesc(BM, 2 * Gp);

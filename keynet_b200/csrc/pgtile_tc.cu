@@ -11,8 +11,19 @@
 //   * under permutation-only keys every pixel multiplies the SAME weight matrix, so the P*Q tap slabs of a channel chunk
 //     are loaded ONCE per chunk by TMA into a slab ring and reused by every pixel of the tile at its own position
 //     (tap of pixel t at union position p = p - t*stride); taps that fall outside the image are simply not issued;
-//   * every pixel has its own fp32 accumulator in TMEM and its own MMA-issuer thread (a thread issues one tcgen05.mma per
-//     ~117 cycles, a 128 x 64 x 8 tf32 MMA occupies the pipe for ~33: one issuer per accumulator keeps the pipe fed);
+//   * every pixel has its own fp32 accumulator in TMEM.  A thread issues one tcgen05.mma per ~85-117 cycles whatever its
+//     shape and a 128 x 64 x 8 tf32 MMA occupies the pipe for ~36, so one instruction per (pixel, tap) leaves the kernel bound
+//     by the issuers' instruction rate (measured: ~850 cycles per pixel-stage for 216 cycles of tensor pipe).  With stride 1
+//     the pixels of one tile ROW that use a gathered position read CONSECUTIVE taps of one tap row (pixel tx at union column
+//     px uses tap dx = px - tx), so with the accumulators of a row laid out in descending tx and the hi (lo) planes of the
+//     tap slabs contiguous in shared memory, ONE tcgen05.mma of N = (pixels in the run) x Gp multiplies the stage by all of
+//     them.  A thread issues one tcgen05.mma per ~143 cycles whatever N and whichever accumulator it targets
+//     (scratch/umma_rate.cu: only N = 256 from one thread, or N = 128 from two, ... reach the pipe rate of 0.56 N cycles), so
+//     what counts is instructions PER ISSUER THREAD: every tile row has two issuers, one per 8-k half of the 16-k stage, both
+//     accumulating into the row's accumulators (zeroed up front: no issuer owns the first write).  2x2 tile, 3x3 taps:
+//     36 instructions per issuer and chunk (54 with one issuer per pixel) against 7.8 k cycles of tensor pipe.  A slab is
+//     waited for once and released once per chunk and issuer (first / last use), not per use.  Other strides: one issuer and
+//     one instruction per (pixel, tap) as before;
 //   * A operand (gathered activations, hi/lo split in registers) in a TMEM ring exactly as in pgroup_tc.cu; 3xTF32
 //     (hi.hi + lo.hi + hi.lo), bias as one extra stage reading the homogeneous row.
 // L2 -> SM bytes per (pixel, 16-channel chunk): G = 64: 108 KB -> 50 KB, G = 96: 126 -> 59, G = 128: 216 -> 120.
@@ -42,11 +53,13 @@ constexpr int kRawStageBytes = KS * BM * 4;      // one gathered stage: 16 rows 
 
 #ifdef KN_TILE_PROF
 __device__ long long g_tile_prof[64];
-#define PROF_T0() const long long pt0_ = clock64()
-#define PROF_ADD(slot) do { if (blockIdx.x == 5000) atomicAdd((unsigned long long *)&g_tile_prof[slot], (unsigned long long)(clock64() - pt0_)); } while (0)
+// fine-grained regions cost ~40 cycles each and perturb the loops they sit in: KN_TILE_PROF is a MASK of the slots to record
+// (bit s / 10 of the mask enables slots 10 s .. 10 s + 9; -DKN_TILE_PROF=1 records only the phase stamps)
+#define PROF_T0(slot) const long long pt0_ = ((KN_TILE_PROF >> ((slot) / 10)) & 1) ? clock64() : 0
+#define PROF_ADD(slot) do { if (((KN_TILE_PROF >> ((slot) / 10)) & 1) && blockIdx.x == 5000) atomicAdd((unsigned long long *)&g_tile_prof[slot], (unsigned long long)(clock64() - pt0_)); } while (0)
 #define PROF_SET(slot) do { if (blockIdx.x == 5000) g_tile_prof[slot] = clock64(); } while (0)
 #else
-#define PROF_T0()
+#define PROF_T0(slot)
 #define PROF_ADD(slot)
 #define PROF_SET(slot)
 #endif
@@ -54,6 +67,7 @@ __device__ long long g_tile_prof[64];
 struct TileGeom {
     int C, G, Gp, th, tw, T, stride, P, Q, n_taps, uh, uw, U_pos, n_chunks;
     int n_slots, n_a, n_raw;           // weight-slab ring (shared memory), activation ring (TMEM) and raw gather ring (shared memory) depths
+    int n_iss, merged, ksplit;         // MMA issuer threads: ksplit per tile row issuing merged runs (stride 1), or one per pixel
     uint32_t a0;                       // first TMEM column of the activation ring (after the T accumulators)
     int slab_bytes, plane_bytes;
     unsigned char pos_order[kMaxPos];  // union positions in issue order: consecutive positions feed DISJOINT sets of pixels (see launch code)
@@ -63,7 +77,7 @@ template <bool RELU, bool PEERS>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const int32_t *__restrict__ tile_cols, const int32_t *__restrict__ tile_rows, int32_t bias_col,
-                  const TileGeom geo, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles,
+                  const TileGeom geo, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles, int first_wave, int stagger_cycles,
                   const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -72,7 +86,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     unsigned char *sp = smem + (size_t)geo.n_slots * geo.slab_bytes + (size_t)geo.n_raw * kRawStageBytes;
     int32_t *s_cols = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)geo.U_pos * geo.C * 4;
     int32_t *s_rows = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)kMaxT * 256 * 4;         // [t][G] output rows of the tile
-    int32_t *s_tap = reinterpret_cast<int32_t *>(sp);                       sp += (size_t)kMaxT * kMaxPos * 4;     // [t][p] -> tap or -1
+    int4 *s_job = reinterpret_cast<int4 *>(sp);                             sp += (size_t)kMaxT * kMaxPos * 16;    // [issuer][o]: what the issuer does at the o-th position of the issue order (see below)
     int32_t *s_valid = reinterpret_cast<int32_t *>(sp);                     sp += (size_t)kMaxPos * 4;
     uint16_t *s_stage = reinterpret_cast<uint16_t *>(sp);                   sp += (size_t)kMaxStages * 2;         // (chunk << 8) | position
     int32_t *s_nstages = reinterpret_cast<int32_t *>(sp);                   sp += 16;
@@ -86,6 +100,13 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Every CTA of a launch takes the same time, so the SMs run in lock step: all epilogues (128 KB of stores per CTA) hit the
+    // memory system together while it idles during the main loops.  The CTAs of the FIRST wave start with a delay of
+    // (blockIdx % 8) / 8 of a CTA's duration, which de-phases the SMs for the rest of the launch.
+    if (stagger_cycles > 0 && (int)blockIdx.x < first_wave) {
+        const long long until = clock64() + (long long)(blockIdx.x & 7) * stagger_cycles;
+        while (clock64() < until) __nanosleep(200);
+    }
     if (tid == 0) PROF_SET(0);
     const KnRaster rt = kn_raster(blockIdx.x, n_sp_tiles, n_btiles, super_tiles);
     const int64_t tile = rt.item;
@@ -93,10 +114,10 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int T = geo.T, C = geo.C, Gp = geo.Gp, U_pos = geo.U_pos;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < geo.n_slots; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], T); }
-        for (int s = 0; s < geo.n_a; s++) { mbar_init(&fullA[s], kGroupThreads); mbar_init(&emptyA[s], T); }
+        for (int s = 0; s < geo.n_slots; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], geo.n_iss); }
+        for (int s = 0; s < geo.n_a; s++) { mbar_init(&fullA[s], kGroupThreads); mbar_init(&emptyA[s], geo.n_iss); }
         for (int s = 0; s < geo.n_raw; s++) { mbar_init(&raw_full[s], 32); mbar_init(&raw_empty[s], kGroupThreads); }
-        mbar_init(accum_bar, T);
+        mbar_init(accum_bar, geo.n_iss);
         fence_barrier_init();
     } else if (warp == 7) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)));
@@ -106,22 +127,49 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int32_t *__restrict__ tc = tile_cols + tile * (int64_t)U_pos * C;
     for (int i = tid; i < U_pos * C; i += kThreads) s_cols[i] = __ldg(tc + i);
     for (int i = tid; i < T * geo.G; i += kThreads) s_rows[(i / geo.G) * 256 + (i % geo.G)] = __ldg(tile_rows + tile * (int64_t)T * geo.G + i);
-    for (int i = tid; i < kMaxT * kMaxPos; i += kThreads) {
-        const int t = i / kMaxPos, p = i - t * kMaxPos;
-        int tap = -1;
-        if (t < T && p < U_pos) {
-            const int ty = t / geo.tw, tx = t - ty * geo.tw, py = p / geo.uw, px = p - py * geo.uw;
-            const int dy = py - ty * geo.stride, dx = px - tx * geo.stride;
-            if (dy >= 0 && dy < geo.P && dx >= 0 && dx < geo.Q) tap = dy * geo.Q + dx;
-        }
-        s_tap[i] = tap;
-    }
     if (tid < kMaxPos) s_valid[tid] = (tid < U_pos && __ldg(tc + (int64_t)tid * C) >= 0) ? 1 : 0;
     __syncthreads();
     {   // list of in-image stages, chunk-major; inside a chunk the positions follow geo.pos_order
         unsigned vmask = 0;                                   // bit i: the i-th position of the issue order lies inside the image
         for (int i = 0; i < U_pos; i++) vmask |= (s_valid[geo.pos_order[i]] ? 1u : 0u) << i;
         const int n_valid = __popc(vmask);
+        // issuer records, one per (issuer, position of the issue order), so that the issuers' loop is a load, two waits, the MMAs
+        // and the commits -- a single thread runs ~4 cycles per dependent instruction, every index computation in that loop
+        // shows up one-to-one in the time per stage:
+        //   x: bit 0 position inside the image | bit 1 this issuer has MMAs here | bit 2 last use of slab (x >> 8 & 255) in the chunk
+        //      | first accumulator column << 16      y: taps read (bit per slab)      z: B descriptor offset      w: instruction descriptor
+        for (int i = tid; i < kMaxT * kMaxPos; i += kThreads) {
+            const int w = i / kMaxPos, o = i - w * kMaxPos;
+            int4 rec = make_int4(0, 0, 0, 0);
+            if (w < geo.n_iss && o < U_pos) {
+                const int p = geo.pos_order[o];
+                const int py = p / geo.uw, px = p - py * geo.uw;
+                int tap0 = -1, m = 0, acc0 = 0, rel = 0;
+                if (geo.merged) {
+                    // issuers of tile row `row` (stride 1): the run of pixels tx_hi .. tx_lo (descending) reads taps dx = px - tx (ascending)
+                    const int row = w / geo.ksplit;
+                    const int dy = py - row;
+                    const int tx_hi = min(px, geo.tw - 1), tx_lo = max(px - geo.Q + 1, 0);
+                    if (dy >= 0 && dy < geo.P && tx_hi >= tx_lo) {
+                        tap0 = dy * geo.Q + (px - tx_hi); m = tx_hi - tx_lo + 1; acc0 = row * geo.tw + (geo.tw - 1 - tx_hi); rel = (tx_hi == geo.tw - 1) ? 1 : 0;
+                    }
+                } else {
+                    const int ty = w / geo.tw, tx = w - ty * geo.tw;
+                    const int dy = py - ty * geo.stride, dx = px - tx * geo.stride;
+                    if (dy >= 0 && dy < geo.P && dx >= 0 && dx < geo.Q) { tap0 = dy * geo.Q + dx; m = 1; acc0 = w; rel = 1; }
+                }
+                const int valid = (vmask >> o) & 1u;
+                if (tap0 >= 0) {
+                    rec.x = valid | (valid << 1) | (rel << 2) | (tap0 << 8) | ((acc0 * Gp) << 16);
+                    rec.y = (int)(((1u << m) - 1u) << tap0);
+                    rec.z = (int)(((uint32_t)tap0 * (uint32_t)geo.plane_bytes) >> 4);          // slab ring of exactly n_taps slots: slot = tap
+                    rec.w = (int)make_idesc(BM, m * Gp);
+                } else {
+                    rec.x = valid;
+                }
+            }
+            s_job[i] = rec;
+        }
         for (int i = tid; i < geo.n_chunks * U_pos; i += kThreads) {
             const int cc = i / U_pos, o = i - cc * U_pos;
             if ((vmask >> o) & 1u) s_stage[cc * n_valid + __popc(vmask & ((1u << o) - 1u))] = (uint16_t)((cc << 8) | geo.pos_order[o]);
@@ -141,77 +189,88 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 
     if (warp == 0) {
         // ===== TMA producer: weight slabs (chunk, tap) in order, then the bias slab =====
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0; uint32_t ph = 0;
             for (int j = 0; j < n_slabs; j++) {
                 const int cc = j / geo.n_taps, tap = j - cc * geo.n_taps;
                 const int k0 = (j == n_slabs - 1) ? geo.n_taps * C : tap * C + cc * KS;
                 mbar_wait(&emptyB[s], ph ^ 1u);
-                unsigned char *bs = smem + (size_t)s * geo.slab_bytes;
+                unsigned char *bs = smem + (size_t)s * geo.plane_bytes;             // hi planes of all slots, then lo planes: consecutive taps are contiguous
                 mbar_arrive_expect_tx(&fullB[s], (uint32_t)geo.slab_bytes);
                 tma_load_2d(bs, &map_hi, k0, 0, &fullB[s]);
-                tma_load_2d(bs + geo.plane_bytes, &map_lo, k0, 0, &fullB[s]);
+                tma_load_2d(bs + (size_t)geo.n_slots * geo.plane_bytes, &map_lo, k0, 0, &fullB[s]);
                 if (++s == geo.n_slots) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp >= 1 && warp <= kMaxT) {
-        // ===== MMA issuers: one elected thread per output pixel of the tile =====
-        const int t = warp - 1;
-        if (lane == 0 && t < T) {
-            const uint32_t idesc = make_idesc(BM, Gp);
-            const uint32_t d = tmem_base + (uint32_t)(t * Gp);
+        // ===== MMA issuers: one elected thread per tile row (merged runs) or per output pixel =====
+        const int w = warp - 1;
+        if (w < geo.n_iss && elect_one()) {
             const uint64_t desc0 = make_desc(smem_u32(smem), 16, 512, kLayoutSW64);
+            const uint64_t lo_off = (uint64_t)(((uint32_t)geo.n_slots * (uint32_t)geo.plane_bytes) >> 4);
+            const int kk0 = w % geo.ksplit;                         // this issuer's 8-k steps of a stage: kk0, kk0 + ksplit, ...
+            const uint32_t a_base = tmem_base + geo.a0;
+            const int4 *jobs = s_job + w * kMaxPos;
             int sa = 0; uint32_t pa = 0;
-            uint32_t started = 0;
-            auto slab_of = [&](int j, int &slot, uint32_t &ph) { const int w = j / geo.n_slots; slot = j - w * geo.n_slots; ph = (uint32_t)(w & 1); };
-            auto issue = [&](int slot) {
-                const uint32_t ta = tmem_base + geo.a0 + (uint32_t)(sa * 32);
-                const uint64_t dslab = desc0 + (uint64_t)(((uint32_t)slot * (uint32_t)geo.slab_bytes) >> 4);
-#pragma unroll
-                for (int kk = 0; kk < KS / 8; kk++) {
+            auto issue = [&](uint32_t d, uint64_t dslab, uint32_t idesc) {     // every accumulator was zeroed by the splitters: always accumulate
+                const uint32_t ta = a_base + (uint32_t)(sa * 32);
+                for (int kk = kk0; kk < KS / 8; kk += geo.ksplit) {
                     const uint64_t db_hi = dslab + (uint64_t)(kk * 2);
-                    const uint64_t db_lo = db_hi + (uint64_t)(geo.plane_bytes >> 4);
-                    umma_tf32_ts(d, ta + kk * 8, db_hi, idesc, started);       // x_hi . w_hi
-                    started = 1u;
-                    umma_tf32_ts(d, ta + 16 + kk * 8, db_hi, idesc, 1u);       // x_lo . w_hi
-                    umma_tf32_ts(d, ta + kk * 8, db_lo, idesc, 1u);            // x_hi . w_lo
+                    umma_tf32_ts(d, ta + kk * 8, db_hi, idesc, 1u);                // x_hi . w_hi
+                    umma_tf32_ts(d, ta + 16 + kk * 8, db_hi, idesc, 1u);           // x_lo . w_hi
+                    umma_tf32_ts(d, ta + kk * 8, db_hi + lo_off, idesc, 1u);       // x_hi . w_lo
                 }
             };
             for (int cc = 0; cc < geo.n_chunks; cc++) {
+                uint32_t waited = 0;                                // slabs of this chunk this issuer has already waited for
+                const uint32_t pb = (uint32_t)(cc & 1);            // slot = tap: a slab's slot is in its cc-th use
                 for (int o = 0; o < U_pos; o++) {
-                    const int p = geo.pos_order[o];
-                    const int tap = s_tap[t * kMaxPos + p];
-                    const bool valid = s_valid[p] != 0;
-                    int slot = 0; uint32_t pb = 0;
-                    if (tap >= 0) {
-                        slab_of(cc * geo.n_taps + tap, slot, pb);
-                        { PROF_T0(); mbar_wait(&fullB[slot], pb); if (t == 0) PROF_ADD(10); }
-                    }
-                    if (valid) {
-                        { PROF_T0(); mbar_wait(&fullA[sa], pa); if (t == 0) PROF_ADD(11); }
+#ifdef KN_TILE_PROF
+                    const long long it0_ = clock64();
+#endif
+                    const int4 r = jobs[o];
+                    if (r.x & 1) {
+                        if (r.x & 2) {
+                            uint32_t need = (uint32_t)r.y & ~waited;
+                            while (need) { const int t = __ffs(need) - 1; need &= need - 1u; PROF_T0(10); mbar_wait(&fullB[t], pb); if (w == 0) PROF_ADD(10); }
+                            waited |= (uint32_t)r.y;
+                        }
+                        { PROF_T0(11); mbar_wait(&fullA[sa], pa); if (w == 0) PROF_ADD(11); }
                         tc_fence_after();
-                        { PROF_T0();
-                        if (tap >= 0) { issue(slot); umma_commit(&emptyB[slot]); }
-                        umma_commit(&emptyA[sa]);
-                        if (t == 0) PROF_ADD(12); }
+                        if (r.x & 2) {
+                            { PROF_T0(12); issue(tmem_base + ((uint32_t)r.x >> 16), desc0 + (uint64_t)(uint32_t)r.z, (uint32_t)r.w); if (w == 0) PROF_ADD(12); }
+                            PROF_T0(14);
+                            if (r.x & 4) umma_commit(&emptyB[(r.x >> 8) & 255]);       // last use of this slab by this issuer in this chunk (waited for above)
+                            umma_commit(&emptyA[sa]);
+                            if (w == 0) PROF_ADD(14);
+                        } else {
+                            mbar_arrive(&emptyA[sa]);                                  // a position this issuer's pixels do not read
+                        }
                         if (++sa == geo.n_a) { sa = 0; pa ^= 1u; }
-                    } else if (tap >= 0) {
-                        mbar_arrive(&emptyB[slot]);                // tap outside the image: release the slab unused
+#ifdef KN_TILE_PROF
+                        if (w == 0 && blockIdx.x == 5000) atomicAdd((unsigned long long *)&g_tile_prof[16], (unsigned long long)(clock64() - it0_));
+#endif
+                    } else if (r.x & 4) {
+                        // position outside the image: the slab's last use does not happen, release it after the earlier ones.  A slab
+                        // is never released before its load has landed (border tiles may not read it at all): the ring's phases
+                        // stay in step and no bulk copy is in flight when the CTA exits
+                        const int t = (r.x >> 8) & 255;
+                        if (!((waited >> t) & 1u)) { mbar_wait(&fullB[t], pb); waited |= 1u << t; }
+                        umma_commit(&emptyB[t]);
                     }
                 }
             }
-            {   // bias stage
-                int slot; uint32_t pb;
-                slab_of(n_slabs - 1, slot, pb);
-                mbar_wait(&fullB[slot], pb);
+            {   // bias stage: every pixel of this issuer reads the one bias slab (slot 0 in its n_chunks-th use)
+                mbar_wait(&fullB[0], (uint32_t)(geo.n_chunks & 1));
                 mbar_wait(&fullA[sa], pa);
                 tc_fence_after();
-                issue(slot);
-                umma_commit(&emptyB[slot]);
+                const int n_acc = geo.merged ? geo.tw : 1;
+                for (int a = 0; a < n_acc; a++) issue(tmem_base + (uint32_t)(((w / geo.ksplit) * n_acc + a) * Gp), desc0, make_idesc(BM, Gp));
+                umma_commit(&emptyB[0]);
                 umma_commit(&emptyA[sa]);
             }
             umma_commit(accum_bar);
-            if (t == 0) PROF_SET(2);
+            if (w == 0) PROF_SET(2);
         }
     } else if (warp == kGatherWarp0 || warp == kGatherWarp0 + 1) {
         // ===== gather warps (alternate stages): X rows of every (position, channel chunk) stage into the raw ring, cp.async 16 B per lane =====
@@ -227,8 +286,8 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const int st = s_stage[i];
             const int cc = st >> 8, p = st & 255;
             const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
-            { PROF_T0(); mbar_wait(&raw_empty[slot], (uint32_t)((wr & 1) ^ 1)); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
-            PROF_T0();
+            { PROF_T0(30); mbar_wait(&raw_empty[slot], (uint32_t)((wr & 1) ^ 1)); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
+            PROF_T0(31);
             float *dst = s_raw + (size_t)slot * (KS * BM) + lane * 4;
             // the 16 row indices first (4 x LDS.128), then 16 back-to-back copies: an index load in front of every copy
             // serialised the warp at ~75 cycles per copy (1200 cycles per stage, measured) instead of the LSU's ~8
@@ -261,13 +320,19 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int q = warp & 3;                                 // TMEM lane quarter
         const int sel = (warp - kProducerWarp0) >> 2;           // splitter group
         const float *src0 = s_raw + q * 32 + lane;
+        if (sel == 0) {                                         // zero the accumulators (ordered before the first MMA by fullA[0], which this group completes)
+            uint32_t z[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) z[j] = 0u;
+            for (int c0 = 0; c0 < T * Gp; c0 += 16) tmem_store<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, z);
+        }
         for (int i = sel; i < n_stages; i += 2) {
             const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
             const int wa = i / geo.n_a, sa = i - wa * geo.n_a;
-            { PROF_T0(); mbar_wait(&raw_full[slot], (uint32_t)(wr & 1)); if (tid == 256) PROF_ADD(20); }
+            { PROF_T0(20); mbar_wait(&raw_full[slot], (uint32_t)(wr & 1)); if (tid == 256) PROF_ADD(20); }
             const float *src = src0 + (size_t)slot * (KS * BM);
             uint32_t hi[KS], lo[KS];
-            { PROF_T0();
+            { PROF_T0(21);
 #pragma unroll
             for (int j = 0; j < KS; j++) {
                 const float v = src[j * BM];
@@ -276,9 +341,9 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
             mbar_arrive(&raw_empty[slot]);                      // the values are in registers: the slot can be refilled
             if (tid == 256) PROF_ADD(21); }
-            { PROF_T0(); mbar_wait(&emptyA[sa], (uint32_t)((wa & 1) ^ 1)); if (tid == 256) PROF_ADD(23); }
+            { PROF_T0(23); mbar_wait(&emptyA[sa], (uint32_t)((wa & 1) ^ 1)); if (tid == 256) PROF_ADD(23); }
             tc_fence_after();
-            PROF_T0();
+            PROF_T0(24);
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + geo.a0 + (uint32_t)(sa * 32);
             tmem_store<KS>(ta, hi);
             tmem_store<KS>(ta + 16, lo);
@@ -297,9 +362,10 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int64_t ne = nbase + q * 32 + lane;
         for (int t = 0; t < T; t++) {
             const int32_t *rg = s_rows + t * 256;
+            const int acc = geo.merged ? (t / geo.tw) * geo.tw + (geo.tw - 1 - t % geo.tw) : t;      // accumulators of a tile row are in descending tx (merged runs)
             for (int c0 = half * 16; c0 < Gp; c0 += 32) {
                 uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Gp + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Gp + c0);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
@@ -383,6 +449,10 @@ conv_tiles_index_kernel(kn_conv2d_desc d, const int32_t *__restrict__ tile_origi
     }
 }
 
+int tile_stagger() {
+    static const int v = getenv("KN_TILE_STAGGER") ? atoi(getenv("KN_TILE_STAGGER")) : 1;
+    return v;
+}
 int tile_super_tiles() {
     static const int v = getenv("KN_TILE_SUPER") ? atoi(getenv("KN_TILE_SUPER")) : 8;
     return v > 0 ? v : 8;
@@ -427,22 +497,24 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     g.uh = (th - 1) * stride + P; g.uw = (tw - 1) * stride + Q; g.U_pos = g.uh * g.uw; g.n_chunks = C / KS;
     KN_REQUIRE(g.T <= kMaxT && g.U_pos <= kMaxPos && g.Gp <= 256, "spmm_tile_tc: tile too large (T=%d positions=%d)", g.T, g.U_pos);
     KN_REQUIRE(g.n_chunks * g.U_pos + 1 <= kMaxStages && g.n_chunks < 255, "spmm_tile_tc: too many stages");
+    g.merged = (stride == 1 && tw * g.Gp <= 256) ? 1 : 0;
+    g.ksplit = (g.merged && 2 * th <= kMaxT) ? 2 : 1;
+    g.n_iss = g.merged ? th * g.ksplit : g.T;
     g.a0 = (uint32_t)(g.T * g.Gp);
     g.n_a = (int)((512 - g.a0) / 32);
     if (g.n_a > 8) g.n_a = 8;
     KN_REQUIRE(g.a0 <= 512 && g.n_a >= 2, "spmm_tile_tc: accumulators of %d pixels x %d rows leave no room for the activation ring", g.T, g.Gp);
     g.plane_bytes = g.Gp * KS * 4;
     g.slab_bytes = 2 * g.plane_bytes;
-    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * 256 * 4 + (size_t)kMaxT * kMaxPos * 4 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
+    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * 256 * 4 + (size_t)kMaxT * kMaxPos * 16 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
     const int64_t avail = 226 * 1024 - (int64_t)fixed;
-    // shared memory: the weight slabs of at least one channel chunk (+1 so the next chunk can start loading), the rest split
-    // between the raw gather ring (bytes in flight towards this SM) and more weight slabs
-    int n_raw = (int)((avail - (int64_t)(g.n_taps + 1) * g.slab_bytes) / kRawStageBytes);
+    // shared memory: the weight slabs of exactly one channel chunk -- slot = tap, so the issuers' descriptors do not depend on the
+    // chunk; a slab is released at its last use inside the chunk, so the next chunk's slabs stream in behind the issuers -- and
+    // the raw gather ring (bytes in flight towards this SM)
+    const int n_slots = g.n_taps;
+    int n_raw = (int)((avail - (int64_t)n_slots * g.slab_bytes) / kRawStageBytes);
     if (n_raw > 16) n_raw = 16;
     KN_REQUIRE(n_raw >= 3, "spmm_tile_tc: the weight slabs of one channel chunk do not fit shared memory (Gp=%d taps=%d)", g.Gp, g.n_taps);
-    int n_slots = (int)((avail - (int64_t)n_raw * kRawStageBytes) / g.slab_bytes);
-    if (n_slots > 3 * g.n_taps) n_slots = 3 * g.n_taps;
-    KN_REQUIRE(n_slots >= g.n_taps + 1, "spmm_tile_tc: the weight slabs of one channel chunk do not fit shared memory (Gp=%d taps=%d)", g.Gp, g.n_taps);
     // issue order of the union positions: raster order (taps are then consumed in the order the slabs load), or -- experiment
     // switch KN_TILE_ORDER=1 -- rounds of positions that feed pairwise DISJOINT pixel sets so that the issuers work on
     // different stages at the same time (measured on B200: 7.30 vs 7.28 ms on VGG16 conv1_2, no gain).
@@ -494,7 +566,10 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     const int super_ = tile_super_tiles();
     const dim3 grid((unsigned)(n_tiles * n_btiles));
     cudaStream_t s = (cudaStream_t)stream;
-#define KN_TILE_LAUNCH(R, PP) pg_tile_tc_kernel<R, PP><<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, n_tiles, n_btiles, super_, X, ldx, Y, ldy, n_vecs, peers)
+    // ~900 cycles per stage (measured): an eighth of a CTA's duration per stagger step
+    const int stagger = tile_stagger() ? (g.n_chunks * g.U_pos + 1) * 900 / 8 * tile_stagger() : 0;
+    const int first_wave = (n_tiles * n_btiles > 2 * (int64_t)kn_sm_count()) ? kn_sm_count() : 0;     // short launches: not worth the delay
+#define KN_TILE_LAUNCH(R, PP) pg_tile_tc_kernel<R, PP><<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, n_tiles, n_btiles, super_, first_wave, stagger, X, ldx, Y, ldy, n_vecs, peers)
     if (peers.n > 0) { if (relu) KN_TILE_LAUNCH(true, true); else KN_TILE_LAUNCH(false, true); }
     else             { if (relu) KN_TILE_LAUNCH(true, false); else KN_TILE_LAUNCH(false, false); }
 #undef KN_TILE_LAUNCH

@@ -26,6 +26,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+// One lane of a converged warp (elect.sync).  The issuer / TMA-producer code runs under THIS predicate, not under
+// `lane == 0`: tcgen05.mma, tcgen05.commit and the bulk-tensor copy are uniform-datapath instructions, and inside a branch
+// the compiler only knows to be divergent it wraps every one of them in an ELECT / 6 x R2UR / BRA.U.ANY loop -- measured
+// 127-143 cycles per tcgen05.mma per thread whatever its shape.  Under elect.sync it emits plain uniform code and one thread
+// issues 128 x N x 8 tf32 MMAs at the pipe rate (42 cycles for N = 64, 74 for N = 128, 138 for N = 256; scratch/umma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -14,6 +14,7 @@ permuted at run time, and the homogeneous coordinate is kept as a local row of o
 
 The planner (`plan_rows`, `LayerShard`) is pure numpy so it is covered by world_size-2 gloo tests on CPU.
 """
+import os
 import numpy as np
 import torch
 from torch import nn
@@ -138,7 +139,7 @@ class ShardedKeyedModel(object):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.fused = bool(fused)
         self.selective = bool(selective)       # fused only: store a row only to the peers whose next layer reads it
-        self.flag_sync = True                  # selective only: neighbourhood flags (kn_peer_sync) instead of a barrier over all ranks per layer
+        self.flag_sync = os.environ.get('KEYNET_B200_FLAG_SYNC', '1') != '0'                  # selective only: neighbourhood flags (kn_peer_sync) instead of a barrier over all ranks per layer
         self._symm = {}
         f_keypair = system.keypair_policy(**keynet_kwargs)
         self.sensor = system.KeyedSensor(inshape, f_keypair('input', inshape))

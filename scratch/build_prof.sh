@@ -1,0 +1,7 @@
+#!/bin/bash
+# library with per-role clock64 accounting in pg_tile_tc_kernel (scratch/tile_prof.py): only pgtile_tc.cu is recompiled
+set -e
+cd "$(dirname "$0")/.."
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -DKN_TILE_PROF=${1:-2} -c -o /tmp/pgtile_tc_prof.o keynet_b200/csrc/pgtile_tc.cu
+objs=$(ls keynet_b200/lib/obj/*.o | grep -v pgtile_tc.o)
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o scratch/libkeynet_b200_prof${1:-2}.so $objs /tmp/pgtile_tc_prof.o

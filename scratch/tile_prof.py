@@ -23,6 +23,7 @@ torch.cuda.synchronize()
 L.kn_debug_tile_prof(out, 0)
 t = list(out)
 print('CTA total %d cycles: prologue %d, issuer0 done at %d, producer loop done at %d, accum ready at %d, epilogue done at %d' % (t[6] - t[0], t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]))
-print('issuer 0: wait fullB %d, wait fullA %d, issue+commit %d' % (t[10], t[11], t[12]))
+print('issuer 0: wait fullB %d, wait fullA %d, fence %d, MMA issue %d, commits %d, arrive (unused stage) %d' % (t[10], t[11], t[13], t[12], t[14], t[15]))
+print('issuer 0: whole valid iterations %d, table loads at the top %d' % (t[16], t[17]))
 print('splitter thread 256 (half the stages): wait raw_full %d, LDS+split %d, wait emptyA %d, STTM+wait+arrive %d' % (t[20], t[21], t[23], t[24]))
 print('gather warp: wait raw_empty %d, issue %d' % (t[30], t[31]))
