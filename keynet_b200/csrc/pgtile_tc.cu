@@ -47,7 +47,6 @@ constexpr int BM = 128;                // batch columns per CTA (UMMA M)
 constexpr int kMaxT = 4;               // output pixels per tile (issuer warps 1-4)
 constexpr int kGatherWarp0 = 5;        // warps 5, 6: activation gathers (alternate stages)
 constexpr int kMaxPos = 32;            // union positions per tile
-constexpr int kMaxStages = 512;
 constexpr int kBiasPos = 255;
 constexpr int kRawStageBytes = KS * BM * 4;      // one gathered stage: 16 rows x 128 batch columns, fp32
 
@@ -68,16 +67,23 @@ struct TileGeom {
     int C, G, Gp, th, tw, T, stride, P, Q, n_taps, uh, uw, U_pos, n_chunks;
     int n_slots, n_a, n_raw;           // weight-slab ring (shared memory), activation ring (TMEM) and raw gather ring (shared memory) depths
     int n_iss, merged, ksplit;         // MMA issuer threads: ksplit per tile row issuing merged runs (stride 1), or one per pixel
+    int bulk_epi, epi_pixels;          // epilogue through shared memory + bulk copies: pixels per pass (0 = per-lane stores)
     uint32_t a0;                       // first TMEM column of the activation ring (after the T accumulators)
     int slab_bytes, plane_bytes;
     unsigned char pos_order[kMaxPos];  // union positions in issue order: consecutive positions feed DISJOINT sets of pixels (see launch code)
 };
 
+// What every issuer does at every position of the issue order -- geometry only, the same for every tile, so it is built on the
+// host and travels as a kernel parameter (constant bank: a uniform load in the issuers' loop):
+//   x: bit 1 this issuer has MMAs here | bit 2 last use of slab (x >> 8 & 255) in the chunk | first accumulator column << 16
+//   y: taps read (bit per slab)      z: B descriptor offset (slot = tap)      w: instruction descriptor
+struct TileJobs { int4 rec[kMaxT * kMaxPos]; };
+
 template <bool RELU, bool PEERS>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const int32_t *__restrict__ tile_cols, const int32_t *__restrict__ tile_rows, int32_t bias_col,
-                  const TileGeom geo, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles, int first_wave, int stagger_cycles,
+                  const TileGeom geo, const __grid_constant__ TileJobs jobs_tab, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles, int first_wave, int stagger_cycles,
                   const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -86,10 +92,6 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     unsigned char *sp = smem + (size_t)geo.n_slots * geo.slab_bytes + (size_t)geo.n_raw * kRawStageBytes;
     int32_t *s_cols = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)geo.U_pos * geo.C * 4;
     int32_t *s_rows = reinterpret_cast<int32_t *>(sp);                      sp += (size_t)kMaxT * 256 * 4;         // [t][G] output rows of the tile
-    int4 *s_job = reinterpret_cast<int4 *>(sp);                             sp += (size_t)kMaxT * kMaxPos * 16;    // [issuer][o]: what the issuer does at the o-th position of the issue order (see below)
-    int32_t *s_valid = reinterpret_cast<int32_t *>(sp);                     sp += (size_t)kMaxPos * 4;
-    uint16_t *s_stage = reinterpret_cast<uint16_t *>(sp);                   sp += (size_t)kMaxStages * 2;         // (chunk << 8) | position
-    int32_t *s_nstages = reinterpret_cast<int32_t *>(sp);                   sp += 16;
     uint64_t *fullB = reinterpret_cast<uint64_t *>(sp);
     uint64_t *emptyB = fullB + geo.n_slots;
     uint64_t *fullA = emptyB + geo.n_slots;
@@ -123,67 +125,18 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // the tile's gather table, the (pixel, position) -> tap table and the list of in-image stages
+    // the tile's gather table and output rows: ONE global round trip and one barrier before every role starts (the stage list and
+    // the issuers' records used to be built here behind a second barrier: 7 k cycles of prologue with the tensor pipe idle)
     const int32_t *__restrict__ tc = tile_cols + tile * (int64_t)U_pos * C;
     for (int i = tid; i < U_pos * C; i += kThreads) s_cols[i] = __ldg(tc + i);
     for (int i = tid; i < T * geo.G; i += kThreads) s_rows[(i / geo.G) * 256 + (i % geo.G)] = __ldg(tile_rows + tile * (int64_t)T * geo.G + i);
-    if (tid < kMaxPos) s_valid[tid] = (tid < U_pos && __ldg(tc + (int64_t)tid * C) >= 0) ? 1 : 0;
-    __syncthreads();
-    {   // list of in-image stages, chunk-major; inside a chunk the positions follow geo.pos_order
-        unsigned vmask = 0;                                   // bit i: the i-th position of the issue order lies inside the image
-        for (int i = 0; i < U_pos; i++) vmask |= (s_valid[geo.pos_order[i]] ? 1u : 0u) << i;
-        const int n_valid = __popc(vmask);
-        // issuer records, one per (issuer, position of the issue order), so that the issuers' loop is a load, two waits, the MMAs
-        // and the commits -- a single thread runs ~4 cycles per dependent instruction, every index computation in that loop
-        // shows up one-to-one in the time per stage:
-        //   x: bit 0 position inside the image | bit 1 this issuer has MMAs here | bit 2 last use of slab (x >> 8 & 255) in the chunk
-        //      | first accumulator column << 16      y: taps read (bit per slab)      z: B descriptor offset      w: instruction descriptor
-        for (int i = tid; i < kMaxT * kMaxPos; i += kThreads) {
-            const int w = i / kMaxPos, o = i - w * kMaxPos;
-            int4 rec = make_int4(0, 0, 0, 0);
-            if (w < geo.n_iss && o < U_pos) {
-                const int p = geo.pos_order[o];
-                const int py = p / geo.uw, px = p - py * geo.uw;
-                int tap0 = -1, m = 0, acc0 = 0, rel = 0;
-                if (geo.merged) {
-                    // issuers of tile row `row` (stride 1): the run of pixels tx_hi .. tx_lo (descending) reads taps dx = px - tx (ascending)
-                    const int row = w / geo.ksplit;
-                    const int dy = py - row;
-                    const int tx_hi = min(px, geo.tw - 1), tx_lo = max(px - geo.Q + 1, 0);
-                    if (dy >= 0 && dy < geo.P && tx_hi >= tx_lo) {
-                        tap0 = dy * geo.Q + (px - tx_hi); m = tx_hi - tx_lo + 1; acc0 = row * geo.tw + (geo.tw - 1 - tx_hi); rel = (tx_hi == geo.tw - 1) ? 1 : 0;
-                    }
-                } else {
-                    const int ty = w / geo.tw, tx = w - ty * geo.tw;
-                    const int dy = py - ty * geo.stride, dx = px - tx * geo.stride;
-                    if (dy >= 0 && dy < geo.P && dx >= 0 && dx < geo.Q) { tap0 = dy * geo.Q + dx; m = 1; acc0 = w; rel = 1; }
-                }
-                const int valid = (vmask >> o) & 1u;
-                if (tap0 >= 0) {
-                    rec.x = valid | (valid << 1) | (rel << 2) | (tap0 << 8) | ((acc0 * Gp) << 16);
-                    rec.y = (int)(((1u << m) - 1u) << tap0);
-                    rec.z = (int)(((uint32_t)tap0 * (uint32_t)geo.plane_bytes) >> 4);          // slab ring of exactly n_taps slots: slot = tap
-                    rec.w = (int)make_idesc(BM, m * Gp);
-                } else {
-                    rec.x = valid;
-                }
-            }
-            s_job[i] = rec;
-        }
-        for (int i = tid; i < geo.n_chunks * U_pos; i += kThreads) {
-            const int cc = i / U_pos, o = i - cc * U_pos;
-            if ((vmask >> o) & 1u) s_stage[cc * n_valid + __popc(vmask & ((1u << o) - 1u))] = (uint16_t)((cc << 8) | geo.pos_order[o]);
-        }
-        if (tid == 0) {
-            s_stage[geo.n_chunks * n_valid] = (uint16_t)((geo.n_chunks << 8) | kBiasPos);    // bias: the homogeneous row against the bias slab
-            *s_nstages = geo.n_chunks * n_valid + 1;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_stages = *s_nstages;
+    unsigned vmask = 0;                                       // bit o: the o-th position of the issue order lies inside the image
+    for (int o = 0; o < U_pos; o++) vmask |= (s_cols[geo.pos_order[o] * C] >= 0 ? 1u : 0u) << o;
+    const int n_stages = geo.n_chunks * __popc(vmask) + 1;    // in-image (chunk, position) stages + the bias stage
     if (tid == 0) PROF_SET(1);
     const int n_slabs = geo.n_chunks * geo.n_taps + 1;
 
@@ -210,7 +163,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const uint64_t lo_off = (uint64_t)(((uint32_t)geo.n_slots * (uint32_t)geo.plane_bytes) >> 4);
             const int kk0 = w % geo.ksplit;                         // this issuer's 8-k steps of a stage: kk0, kk0 + ksplit, ...
             const uint32_t a_base = tmem_base + geo.a0;
-            const int4 *jobs = s_job + w * kMaxPos;
+            const int4 *jobs = jobs_tab.rec + w * kMaxPos;
             int sa = 0; uint32_t pa = 0;
             auto issue = [&](uint32_t d, uint64_t dslab, uint32_t idesc) {     // every accumulator was zeroed by the splitters: always accumulate
                 const uint32_t ta = a_base + (uint32_t)(sa * 32);
@@ -229,7 +182,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     const long long it0_ = clock64();
 #endif
                     const int4 r = jobs[o];
-                    if (r.x & 1) {
+                    if ((vmask >> o) & 1u) {
                         if (r.x & 2) {
                             uint32_t need = (uint32_t)r.y & ~waited;
                             while (need) { const int t = __ffs(need) - 1; need &= need - 1u; PROF_T0(10); mbar_wait(&fullB[t], pb); if (w == 0) PROF_ADD(10); }
@@ -282,9 +235,19 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const bool col_ok = ncol < n_vecs;                      // n_vecs % 4 == 0: a chunk is entirely inside or outside
         const float *__restrict__ xcol = X + (col_ok ? ncol : 0);
         const int bytes = col_ok ? 16 : 0;                      // src-size 0 => 16 bytes of zeros
-        for (int i = warp - kGatherWarp0; i < n_stages; i += 2) {
-            const int st = s_stage[i];
-            const int cc = st >> 8, p = st & 255;
+        const int mine = warp - kGatherWarp0;
+        int i = -1, cc = 0, o = -1;                              // stage counter and its (chunk, position of the issue order)
+        while (true) {
+            // next in-image stage, chunk-major; after the last chunk the bias stage
+            int p;
+            ++i;
+            if (i == n_stages - 1) p = kBiasPos;
+            else if (i >= n_stages) break;
+            else {
+                do { if (++o == U_pos) { o = 0; ++cc; } } while (!((vmask >> o) & 1u));
+                p = geo.pos_order[o];
+            }
+            if ((i & 1) != mine) continue;
             const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
             { PROF_T0(30); mbar_wait(&raw_empty[slot], (uint32_t)((wr & 1) ^ 1)); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
             PROF_T0(31);
@@ -360,17 +323,67 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         if (tid == 256) PROF_SET(4);
         const int half = sel;                                    // two warps per lane quarter: even / odd 16-column chunks
         const int64_t ne = nbase + q * 32 + lane;
+        if (!PEERS && geo.bulk_epi) {
+            // Output rows through shared memory and bulk copies.  With per-lane stores (below) a warp instruction writes one
+            // 128-byte piece of a row and the SM's queue of outstanding stores, not bandwidth, set the pace: 128 KB per CTA took
+            // ~10 k cycles (70 per STG, measured), a sixth of the CTA, with nothing else to run on the SM.  Here the accumulators
+            // are transposed into [row][128 batch columns] in the (now idle) gather ring, and every row leaves as ONE 512-byte
+            // cp.async.bulk; the CTA only waits until shared memory has been read, not until the writes have landed.
+            float *stage = s_raw;
+            const int e = tid - kProducerWarp0 * 32;             // 0 .. 255
+            const int ppp = geo.epi_pixels;                      // pixels per pass (what fits the ring)
+            const uint32_t row_bytes = (uint32_t)((n_vecs - nbase < BM ? n_vecs - nbase : BM) * 4);
+            for (int t0 = 0; t0 < T; t0 += ppp) {
+                const int tn = (T - t0 < ppp) ? T - t0 : ppp;
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // the ring is idle (both splitter groups done) / the previous pass has been read
+                for (int tl = 0; tl < tn; tl++) {
+                    const int t = t0 + tl;
+                    const int acc = geo.merged ? (t / geo.tw) * geo.tw + (geo.tw - 1 - t % geo.tw) : t;
+                    for (int c0 = half * 16; c0 < Gp; c0 += 32) {
+                        uint32_t r[16];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Gp + c0);
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                                     : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float *dst = stage + (size_t)(tl * geo.G + c0) * BM + q * 32 + lane;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if (c0 + j < geo.G) {
+                                float y = __uint_as_float(r[j]);
+                                if (RELU) y = fmaxf(y, 0.0f);
+                                dst[j * BM] = y;
+                            }
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copies
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = e; i < tn * geo.G; i += 256) {
+                    const int tl = i / geo.G, c = i - tl * geo.G;
+                    float *gdst = Y + (int64_t)s_rows[(t0 + tl) * 256 + c] * ldy + nbase;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(gdst), "r"(smem_u32(stage + (size_t)i * BM)), "r"(row_bytes) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else
         for (int t = 0; t < T; t++) {
             const int32_t *rg = s_rows + t * 256;
             const int acc = geo.merged ? (t / geo.tw) * geo.tw + (geo.tw - 1 - t % geo.tw) : t;      // accumulators of a tile row are in descending tx (merged runs)
             for (int c0 = half * 16; c0 < Gp; c0 += 32) {
                 uint32_t r[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Gp + c0);
+                { PROF_T0(40);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (tid == 256) PROF_ADD(40); }
+                PROF_T0(41);
                 if (ne < n_vecs) {
                     if constexpr (!PEERS) {
 #pragma unroll
@@ -402,6 +415,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         }
                     }
                 }
+                if (tid == 256) PROF_ADD(41);
             }
         }
     }
@@ -496,7 +510,6 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     g.C = C; g.G = G; g.Gp = ((G + 15) / 16) * 16; g.th = th; g.tw = tw; g.T = th * tw; g.stride = stride; g.P = P; g.Q = Q; g.n_taps = P * Q;
     g.uh = (th - 1) * stride + P; g.uw = (tw - 1) * stride + Q; g.U_pos = g.uh * g.uw; g.n_chunks = C / KS;
     KN_REQUIRE(g.T <= kMaxT && g.U_pos <= kMaxPos && g.Gp <= 256, "spmm_tile_tc: tile too large (T=%d positions=%d)", g.T, g.U_pos);
-    KN_REQUIRE(g.n_chunks * g.U_pos + 1 <= kMaxStages && g.n_chunks < 255, "spmm_tile_tc: too many stages");
     g.merged = (stride == 1 && tw * g.Gp <= 256) ? 1 : 0;
     g.ksplit = (g.merged && 2 * th <= kMaxT) ? 2 : 1;
     g.n_iss = g.merged ? th * g.ksplit : g.T;
@@ -506,7 +519,7 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     KN_REQUIRE(g.a0 <= 512 && g.n_a >= 2, "spmm_tile_tc: accumulators of %d pixels x %d rows leave no room for the activation ring", g.T, g.Gp);
     g.plane_bytes = g.Gp * KS * 4;
     g.slab_bytes = 2 * g.plane_bytes;
-    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * 256 * 4 + (size_t)kMaxT * kMaxPos * 16 + kMaxPos * 4 + kMaxStages * 2 + 16 + 1024 /*align*/ + 1024 /*barriers*/;
+    const size_t fixed = (size_t)g.U_pos * C * 4 + (size_t)kMaxT * 256 * 4 + 1024 /*align*/ + 1024 /*barriers*/;
     const int64_t avail = 226 * 1024 - (int64_t)fixed;
     // shared memory: the weight slabs of exactly one channel chunk -- slot = tap, so the issuers' descriptors do not depend on the
     // chunk; a slab is released at its last use inside the chunk, so the next chunk's slabs stream in behind the issuers -- and
@@ -550,6 +563,10 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     KN_REQUIRE((size_t)(2 * n_slots + 2 * g.n_a + 2 * n_raw + 2) * 8 <= 1024, "spmm_tile_tc: too many barriers");
     g.n_slots = n_slots;
     g.n_raw = n_raw;
+    static const int bulk = getenv("KN_TILE_BULK") ? atoi(getenv("KN_TILE_BULK")) : 1;
+    g.epi_pixels = (int)(((int64_t)n_raw * kRawStageBytes) / ((int64_t)G * BM * 4));
+    if (g.epi_pixels > g.T) g.epi_pixels = g.T;
+    g.bulk_epi = (bulk && g.epi_pixels >= 1 && (((uintptr_t)Y) & 15) == 0 && ldy % 4 == 0) ? 1 : 0;
     const size_t smem = (size_t)n_slots * g.slab_bytes + (size_t)n_raw * kRawStageBytes + fixed;
     const int64_t n_btiles = kn_cdiv(n_vecs, BM);
     KN_REQUIRE(n_tiles * n_btiles <= 0x7fffffffLL, "spmm_tile_tc: grid too large");
@@ -558,6 +575,35 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
         KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    TileJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    for (int w = 0; w < g.n_iss; w++) {
+        for (int o = 0; o < g.U_pos; o++) {
+            const int p = g.pos_order[o];
+            const int py = p / g.uw, px = p - py * g.uw;
+            int tap0 = -1, m = 0, acc0 = 0, rel = 0;
+            if (g.merged) {
+                // issuers of tile row `row` (stride 1): the run of pixels tx_hi .. tx_lo (descending) reads taps dx = px - tx (ascending);
+                // a slab's last use in a chunk is by the row's last pixel
+                const int row = w / g.ksplit;
+                const int dy = py - row;
+                const int tx_hi = px < g.tw - 1 ? px : g.tw - 1, tx_lo = px - g.Q + 1 > 0 ? px - g.Q + 1 : 0;
+                if (dy >= 0 && dy < g.P && tx_hi >= tx_lo) {
+                    tap0 = dy * g.Q + (px - tx_hi); m = tx_hi - tx_lo + 1; acc0 = row * g.tw + (g.tw - 1 - tx_hi); rel = (tx_hi == g.tw - 1) ? 1 : 0;
+                }
+            } else {
+                const int ty = w / g.tw, tx = w - ty * g.tw;
+                const int dy = py - ty * g.stride, dx = px - tx * g.stride;
+                if (dy >= 0 && dy < g.P && dx >= 0 && dx < g.Q) { tap0 = dy * g.Q + dx; m = 1; acc0 = w; rel = 1; }
+            }
+            if (tap0 < 0) continue;
+            int4 &rec = jobs.rec[w * kMaxPos + o];
+            rec.x = 2 | (rel << 2) | (tap0 << 8) | ((acc0 * g.Gp) << 16);
+            rec.y = (int)(((1u << m) - 1u) << tap0);
+            rec.z = (int)(((uint32_t)tap0 * (uint32_t)g.plane_bytes) >> 4);          // slab ring of exactly n_taps slots: slot = tap
+            rec.w = (int)make_idesc(BM, m * g.Gp);
+        }
     }
     CUtensorMap maps[4];
     memcpy(maps, maps_host, 4 * sizeof(CUtensorMap));
@@ -569,7 +615,7 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     // ~900 cycles per stage (measured): an eighth of a CTA's duration per stagger step
     const int stagger = tile_stagger() ? (g.n_chunks * g.U_pos + 1) * 900 / 8 * tile_stagger() : 0;
     const int first_wave = (n_tiles * n_btiles > 2 * (int64_t)kn_sm_count()) ? kn_sm_count() : 0;     // short launches: not worth the delay
-#define KN_TILE_LAUNCH(R, PP) pg_tile_tc_kernel<R, PP><<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, n_tiles, n_btiles, super_, first_wave, stagger, X, ldx, Y, ldy, n_vecs, peers)
+#define KN_TILE_LAUNCH(R, PP) pg_tile_tc_kernel<R, PP><<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, jobs, n_tiles, n_btiles, super_, first_wave, stagger, X, ldx, Y, ldy, n_vecs, peers)
     if (peers.n > 0) { if (relu) KN_TILE_LAUNCH(true, true); else KN_TILE_LAUNCH(false, true); }
     else             { if (relu) KN_TILE_LAUNCH(true, false); else KN_TILE_LAUNCH(false, false); }
 #undef KN_TILE_LAUNCH

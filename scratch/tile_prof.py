@@ -27,3 +27,4 @@ print('issuer 0: wait fullB %d, wait fullA %d, fence %d, MMA issue %d, commits %
 print('issuer 0: whole valid iterations %d, table loads at the top %d' % (t[16], t[17]))
 print('splitter thread 256 (half the stages): wait raw_full %d, LDS+split %d, wait emptyA %d, STTM+wait+arrive %d' % (t[20], t[21], t[23], t[24]))
 print('gather warp: wait raw_empty %d, issue %d' % (t[30], t[31]))
+print('epilogue thread 256: tcgen05.ld + wait %d, stores %d' % (t[40], t[41]))
