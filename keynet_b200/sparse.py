@@ -37,18 +37,42 @@ class MonomialKey(object):
         """bias (optional, homogeneous keys only): extra entries A[r, n-1] = bias[r] for r < n-1 -- the affine
         photometric keys [[D, b],[0, 1]] (keynet/sparse.py:99-119).  Keys with a bias column are closed under
         products, so the whole photometric key family stays O(n) on the host."""
-        self.perm = np.ascontiguousarray(perm, dtype=np.int64)
-        n = len(self.perm)
-        self.scale = np.ones(n, dtype=np.float32) if scale is None else np.ascontiguousarray(scale, dtype=np.float32)
-        assert self.scale.shape == (n,)
+        self._perm = np.ascontiguousarray(perm, dtype=np.int64)
+        n = len(self._perm)
+        self._scale = None if scale is None else np.ascontiguousarray(scale, dtype=np.float32)       # None: all ones (materialised on demand)
+        assert self._scale is None or self._scale.shape == (n,)
         self.bias = None
         if bias is not None:
             b = np.ascontiguousarray(bias, dtype=np.float32).reshape(-1)
-            assert b.shape == (n,) and b[-1] == 0 and self.perm[-1] == n - 1, 'bias needs a homogeneous key (last row e_last)'
+            assert b.shape == (n,) and b[-1] == 0 and self._perm[-1] == n - 1, 'bias needs a homogeneous key (last row e_last)'
             self.bias = b
+        self._n = n
+        self._unpermuted = None          # structure tests are evaluated once: keys are immutable once built
+        self._unscaled = True if scale is None else None
         self.shape = (n, n)
         self.dtype = np.float32
         self.ndim = 2
+
+    @classmethod
+    def identity(cls, n):
+        """The n x n identity without its index / value arrays (built on first use): most factors of keygen's
+        A = C^-1 . p . g . P . G . C are identities, and for VGG16 every one of them used to cost two 3.2 M element arrays."""
+        K = cls.__new__(cls)
+        (K._perm, K._scale, K.bias, K._n, K._unpermuted, K._unscaled) = (None, None, None, int(n), True, True)
+        (K.shape, K.dtype, K.ndim) = ((int(n), int(n)), np.float32, 2)
+        return K
+
+    @property
+    def perm(self):
+        if self._perm is None:
+            self._perm = np.arange(self._n, dtype=np.int64)
+        return self._perm
+
+    @property
+    def scale(self):
+        if self._scale is None:
+            self._scale = np.ones(self._n, dtype=np.float32)
+        return self._scale
 
     def has_bias(self):
         return self.bias is not None
@@ -58,23 +82,23 @@ class MonomialKey(object):
 
     # -- structure tests
     def is_unpermuted(self):
-        return bool(np.array_equal(self.perm, np.arange(len(self.perm))))
+        if self._unpermuted is None:
+            self._unpermuted = bool(np.array_equal(self._perm, np.arange(self._n)))
+        return self._unpermuted
 
     def is_unscaled(self):
-        return bool(np.all(self.scale == np.float32(1.0)))
+        if self._unscaled is None:
+            self._unscaled = bool(np.all(self._scale == np.float32(1.0)))
+        return self._unscaled
 
     def is_identity(self):
         return self.is_unpermuted() and self.is_unscaled() and self.bias is None
 
-    def _identity(self):
-        """is_identity(), evaluated once (keys are immutable once built)."""
-        if getattr(self, '_ident', None) is None:
-            self._ident = self.is_identity()
-        return self._ident
+    _identity = is_identity
 
     @property
     def nnz(self):
-        return len(self.perm)
+        return self._n
 
     # -- algebra (fp32 products rounded once, like scipy's csr_matmat on single-entry rows)
     def dot(self, other):
@@ -94,7 +118,14 @@ class MonomialKey(object):
                 bb = np.zeros(len(self.perm), dtype=np.float32) if other.bias is None else (self.scale * other.bias[self.perm]).astype(np.float32)
                 bias = bb if self.bias is None else (bb + self.bias).astype(np.float32)
                 bias[-1] = 0
-            return MonomialKey(other.perm[self.perm], (self.scale * other.scale[self.perm]).astype(np.float32), bias)
+            if self.is_unscaled() and other.is_unscaled():
+                scale = None                                   # 1 * 1: no value array
+            elif other.is_unscaled():
+                scale = self.scale
+            else:
+                scale = (self.scale * other.scale[self.perm]).astype(np.float32)
+            perm = other.perm if self.is_unpermuted() else (self.perm if other.is_unpermuted() else other.perm[self.perm])
+            return MonomialKey(perm, scale, bias)
         if isinstance(other, SparseMatrix):
             return other._left_monomial(self)
         if isinstance(other, SparseKey):
@@ -111,9 +142,14 @@ class MonomialKey(object):
 
     def transpose(self):
         assert self.bias is None, 'a key with a bias column has no monomial transpose (use the inverse from the generator)'
-        n = len(self.perm)
-        (perm, scale) = (np.empty(n, dtype=np.int64), np.empty(n, dtype=np.float32))
+        n = self._n
+        if self.is_unpermuted():
+            return self                                        # diagonal: its own transpose
+        perm = np.empty(n, dtype=np.int64)
         perm[self.perm] = np.arange(n)
+        if self.is_unscaled():
+            return MonomialKey(perm)
+        scale = np.empty(n, dtype=np.float32)
         scale[self.perm] = self.scale
         return MonomialKey(perm, scale)
 
@@ -282,11 +318,11 @@ def is_key(A):
 
 
 def sparse_identity_matrix(n, dtype=np.float32):
-    return MonomialKey(np.arange(int(n)))
+    return MonomialKey.identity(n)
 
 
 def sparse_identity_matrix_like(A):
-    return MonomialKey(np.arange(A.shape[0]))
+    return MonomialKey.identity(A.shape[0])
 
 
 def sparse_permutation_matrix(n, dtype=np.float32, withinverse=False):
@@ -352,7 +388,17 @@ def sparse_affine_to_linear(A, bias=None, dtype=np.float32):
         bias = np.asarray(bias).reshape(-1)
         assert bias.shape[0] == n
         b = np.concatenate([bias.astype(np.float32), np.zeros(1, dtype=np.float32)])
-    return MonomialKey(np.concatenate([A.perm, [n]]), np.concatenate([A.scale, np.ones(1, dtype=np.float32)]), b)
+    if b is None and A.is_identity():
+        return MonomialKey.identity(n + 1)
+    perm = np.empty(n + 1, dtype=np.int64)
+    perm[:n] = A.perm
+    perm[n] = n
+    scale = None
+    if not A.is_unscaled():
+        scale = np.empty(n + 1, dtype=np.float32)
+        scale[:n] = A.scale
+        scale[n] = 1.0
+    return MonomialKey(perm, scale, b)
 
 
 def diagonal_affine_to_linear(A, bias=None, withinverse=False, dtype=np.float32):
@@ -1266,7 +1312,8 @@ def _remapped(Ainv, col_remap, n_cols_phys):
     assert len(col_remap) == Ainv.shape[0] and n_cols_phys > int(col_remap.max())
     K = MonomialKey(Ainv.perm, Ainv.scale, Ainv.bias)          # the bias column rides along: position[R] is the last physical row
     assert Ainv.bias is None or int(col_remap[-1]) == int(n_cols_phys) - 1, 'homogeneous coordinate must stay the last gathered row'
-    K.perm = col_remap[Ainv.perm]            # no longer square: only used as (col_map, col_scale, col_bias) by _keycompile
+    K._perm = col_remap[Ainv.perm]           # no longer square: only used as (col_map, col_scale, col_bias) by _keycompile
+    K._unpermuted = False
     K.shape = (Ainv.shape[0], int(n_cols_phys))
     return (K, int(n_cols_phys))
 
