@@ -79,11 +79,52 @@ struct TileGeom {
 //   y: taps read (bit per slab)      z: B descriptor offset (slot = tap)      w: instruction descriptor
 struct TileJobs { int4 rec[kMaxT * kMaxPos]; };
 
-template <bool RELU, bool PEERS>
+// Issuer loop for the common geometries (3x3 taps, stride 1, merged runs, two issuers per tile row), everything that only
+// depends on the geometry folded at compile time.  An issuer is ONE thread: at ~4-6 cycles per dependent scalar instruction
+// the ~90 instructions per stage of the table-driven loop (record load, bit tests, descriptor arithmetic, ring bookkeeping)
+// were 565 cycles per stage against 523 cycles of tensor pipe -- the issuers, not the pipe, set the pace.  Interior tiles
+// (every position inside the image) take this path; border tiles the generic loop.
+template <int TH, int TW, int GP, int ROW, int KK0>
+__device__ __forceinline__ void issuer_fast(int n_chunks, int n_a, uint32_t tmem_base, uint32_t a_base, uint64_t desc0,
+                                            uint64_t *fullA, uint64_t *emptyA, uint64_t *fullB, uint64_t *emptyB, int &sa, uint32_t &pa)
+{
+    constexpr int UW = TW + 2, UH = TH + 2;
+    constexpr uint64_t lo_off = (uint64_t)((9u * GP * 64u) >> 4);           // 9 slots (slot = tap) of hi planes, then the lo planes
+    for (int cc = 0; cc < n_chunks; cc++) {
+        const uint32_t pb = (uint32_t)(cc & 1);
+#pragma unroll
+        for (int o = 0; o < UH * UW; o++) {
+            const int py = o / UW, px = o % UW, dy = py - ROW;
+            const int tx_hi = px < TW - 1 ? px : TW - 1, tx_lo = px - 2 > 0 ? px - 2 : 0;
+            if (dy >= 0 && dy < 3 && tx_hi >= tx_lo) {
+                const int tap0 = dy * 3 + (px - tx_hi), m = tx_hi - tx_lo + 1, acc0 = ROW * TW + (TW - 1 - tx_hi);
+                if (px < 3) mbar_wait(&fullB[dy * 3 + px], pb);            // the one slab first read here (pixel 0's tap); the others were read before
+                mbar_wait(&fullA[sa], pa);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc0 * GP);
+                const uint32_t ta = a_base + (uint32_t)(sa * 32 + KK0 * 8);
+                const uint64_t db_hi = desc0 + (uint64_t)((((uint32_t)tap0 * GP * 64u) >> 4) + KK0 * 2);
+                constexpr uint32_t dummy = 0; (void)dummy;
+                const uint32_t idesc = make_idesc(BM, m * GP);
+                umma_tf32_ts(d, ta, db_hi, idesc, 1u);                      // x_hi . w_hi
+                umma_tf32_ts(d, ta + 16, db_hi, idesc, 1u);                 // x_lo . w_hi
+                umma_tf32_ts(d, ta, db_hi + lo_off, idesc, 1u);             // x_hi . w_lo
+                if (tx_hi == TW - 1) umma_commit(&emptyB[tap0]);            // last use of this slab by this issuer in this chunk
+                umma_commit(&emptyA[sa]);
+            } else {
+                mbar_wait(&fullA[sa], pa);
+                mbar_arrive(&emptyA[sa]);
+            }
+            if (++sa == n_a) { sa = 0; pa ^= 1u; }
+        }
+    }
+}
+
+template <bool RELU, bool PEERS, int TH, int TW, int GP>
 __global__ void __launch_bounds__(kThreads, 1)
 pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const int32_t *__restrict__ tile_cols, const int32_t *__restrict__ tile_rows, int32_t bias_col,
-                  const TileGeom geo, const __grid_constant__ TileJobs jobs_tab, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles, int first_wave, int stagger_cycles,
+                  const TileGeom geo, const __grid_constant__ TileJobs jobs_tab, int64_t n_sp_tiles, int64_t n_btiles, int super_tiles,
                   const float *__restrict__ X, int64_t ldx, float *__restrict__ Y, int64_t ldy, int64_t n_vecs, const __grid_constant__ KnPeers peers)
 {
     extern __shared__ unsigned char smem_dyn[];
@@ -102,13 +143,6 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // Every CTA of a launch takes the same time, so the SMs run in lock step: all epilogues (128 KB of stores per CTA) hit the
-    // memory system together while it idles during the main loops.  The CTAs of the FIRST wave start with a delay of
-    // (blockIdx % 8) / 8 of a CTA's duration, which de-phases the SMs for the rest of the launch.
-    if (stagger_cycles > 0 && (int)blockIdx.x < first_wave) {
-        const long long until = clock64() + (long long)(blockIdx.x & 7) * stagger_cycles;
-        while (clock64() < until) __nanosleep(200);
-    }
     if (tid == 0) PROF_SET(0);
     const KnRaster rt = kn_raster(blockIdx.x, n_sp_tiles, n_btiles, super_tiles);
     const int64_t tile = rt.item;
@@ -174,7 +208,19 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     umma_tf32_ts(d, ta + kk * 8, db_hi + lo_off, idesc, 1u);       // x_hi . w_lo
                 }
             };
-            for (int cc = 0; cc < geo.n_chunks; cc++) {
+            bool fast = false;
+            if constexpr (TH > 0) {
+                if (vmask == (1u << ((TH + 2) * (TW + 2))) - 1u) {      // interior tile
+                    fast = true;
+                    switch (w) {
+                    case 0: issuer_fast<TH, TW, GP, 0, 0>(geo.n_chunks, geo.n_a, tmem_base, a_base, desc0, fullA, emptyA, fullB, emptyB, sa, pa); break;
+                    case 1: issuer_fast<TH, TW, GP, 0, 1>(geo.n_chunks, geo.n_a, tmem_base, a_base, desc0, fullA, emptyA, fullB, emptyB, sa, pa); break;
+                    case 2: if constexpr (TH > 1) issuer_fast<TH, TW, GP, 1, 0>(geo.n_chunks, geo.n_a, tmem_base, a_base, desc0, fullA, emptyA, fullB, emptyB, sa, pa); break;
+                    default: if constexpr (TH > 1) issuer_fast<TH, TW, GP, 1, 1>(geo.n_chunks, geo.n_a, tmem_base, a_base, desc0, fullA, emptyA, fullB, emptyB, sa, pa); break;
+                    }
+                }
+            }
+            for (int cc = 0; cc < (fast ? 0 : geo.n_chunks); cc++) {
                 uint32_t waited = 0;                                // slabs of this chunk this issuer has already waited for
                 const uint32_t pb = (uint32_t)(cc & 1);            // slot = tap: a slab's slot is in its cc-th use
                 for (int o = 0; o < U_pos; o++) {
@@ -463,10 +509,6 @@ conv_tiles_index_kernel(kn_conv2d_desc d, const int32_t *__restrict__ tile_origi
     }
 }
 
-int tile_stagger() {
-    static const int v = getenv("KN_TILE_STAGGER") ? atoi(getenv("KN_TILE_STAGGER")) : 1;
-    return v;
-}
 int tile_super_tiles() {
     static const int v = getenv("KN_TILE_SUPER") ? atoi(getenv("KN_TILE_SUPER")) : 8;
     return v > 0 ? v : 8;
@@ -570,12 +612,6 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     const size_t smem = (size_t)n_slots * g.slab_bytes + (size_t)n_raw * kRawStageBytes + fixed;
     const int64_t n_btiles = kn_cdiv(n_vecs, BM);
     KN_REQUIRE(n_tiles * n_btiles <= 0x7fffffffLL, "spmm_tile_tc: grid too large");
-    KN_ONCE_PER_DEVICE {
-        KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        KN_CUDA(cudaFuncSetAttribute(pg_tile_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    }
     TileJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     for (int w = 0; w < g.n_iss; w++) {
@@ -612,13 +648,20 @@ KN_API int kn_spmm_tile_tc_f32(const void *maps_host, const int32_t *tile_cols, 
     const int super_ = tile_super_tiles();
     const dim3 grid((unsigned)(n_tiles * n_btiles));
     cudaStream_t s = (cudaStream_t)stream;
-    // ~900 cycles per stage (measured): an eighth of a CTA's duration per stagger step
-    const int stagger = tile_stagger() ? (g.n_chunks * g.U_pos + 1) * 900 / 8 * tile_stagger() : 0;
-    const int first_wave = (n_tiles * n_btiles > 2 * (int64_t)kn_sm_count()) ? kn_sm_count() : 0;     // short launches: not worth the delay
-#define KN_TILE_LAUNCH(R, PP) pg_tile_tc_kernel<R, PP><<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, jobs, n_tiles, n_btiles, super_, first_wave, stagger, X, ldx, Y, ldy, n_vecs, peers)
+    // geometry-specialised issuers (issuer_fast) for 3x3 / stride-1 layers with the tile shapes the host picks
+    const bool spec_ok = g.merged && g.ksplit == 2 && P == 3 && Q == 3 && stride == 1 && g.n_slots == 9;
+    const int spec = !spec_ok ? 0 : (th == 2 && tw == 2 && g.Gp == 64) ? 1 : (th == 2 && tw == 2 && g.Gp == 96) ? 2 : (th == 1 && tw == 2 && g.Gp == 128) ? 3 : 0;
+#define KN_TILE_LAUNCH2(R, PP, A, B, C) do { \
+        auto kfn = pg_tile_tc_kernel<R, PP, A, B, C>; \
+        KN_ONCE_PER_DEVICE { KN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); } \
+        kfn<<<grid, kThreads, smem, s>>>(maps[0], maps[1], tile_cols, tile_rows, bias_col, g, jobs, n_tiles, n_btiles, super_, X, ldx, Y, ldy, n_vecs, peers); } while (0)
+#define KN_TILE_LAUNCH(R, PP) do { \
+        if (spec == 1) KN_TILE_LAUNCH2(R, PP, 2, 2, 64); else if (spec == 2) KN_TILE_LAUNCH2(R, PP, 2, 2, 96); \
+        else if (spec == 3) KN_TILE_LAUNCH2(R, PP, 1, 2, 128); else KN_TILE_LAUNCH2(R, PP, 0, 0, 0); } while (0)
     if (peers.n > 0) { if (relu) KN_TILE_LAUNCH(true, true); else KN_TILE_LAUNCH(false, true); }
     else             { if (relu) KN_TILE_LAUNCH(true, false); else KN_TILE_LAUNCH(false, false); }
 #undef KN_TILE_LAUNCH
+#undef KN_TILE_LAUNCH2
     KN_CHECK_LAUNCH();
     return KN_OK;
 }
