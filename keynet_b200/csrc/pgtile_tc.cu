@@ -39,13 +39,18 @@
 namespace {
 using namespace kn_tc;
 
-constexpr int kThreads = 512;          // warp 0: TMA (weight slabs)  warps 1-4: MMA issuers  warps 5-6: activation gathers (cp.async)  warp 7: TMEM alloc  warps 8-15: hi/lo splitters + epilogue
+#ifndef KN_TILE_GATHER_WARPS
+#define KN_TILE_GATHER_WARPS 7
+#endif
+constexpr int kGatherWarps = KN_TILE_GATHER_WARPS;
+constexpr int kProducerWarp0 = 12;     // first splitter warp: a multiple of 4 (a warp reaches the TMEM lanes of its quarter, warp % 4)
+constexpr int kThreads = (kProducerWarp0 + 8) * 32;   // warp 0: TMA (weight slabs)  warps 1-4: MMA issuers  warps 5..: activation gathers (cp.async; warp 7 first allocates TMEM)  warps 12-19: hi/lo splitters + epilogue
 constexpr int kGroupThreads = 128;     // the 8 splitter warps work as two groups of 4 (one warp per TMEM lane quarter) on alternate stages
-constexpr int kProducerWarp0 = 8;
 constexpr int KS = 16;                 // k per stage = channels per chunk
 constexpr int BM = 128;                // batch columns per CTA (UMMA M)
 constexpr int kMaxT = 4;               // output pixels per tile (issuer warps 1-4)
-constexpr int kGatherWarp0 = 5;        // warps 5, 6: activation gathers (alternate stages)
+constexpr int kGatherWarp0 = 5;        // warps 5 .. 5 + kGatherWarps - 1: activation gathers (stages round-robin)
+static_assert(kGatherWarp0 + kGatherWarps <= kProducerWarp0, "gather warps overlap the splitters");
 constexpr int kMaxPos = 32;            // union positions per tile
 constexpr int kBiasPos = 255;
 constexpr int kRawStageBytes = KS * BM * 4;      // one gathered stage: 16 rows x 128 batch columns, fp32
@@ -271,7 +276,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             umma_commit(accum_bar);
             if (w == 0) PROF_SET(2);
         }
-    } else if (warp == kGatherWarp0 || warp == kGatherWarp0 + 1) {
+    } else if (warp >= kGatherWarp0 && warp < kGatherWarp0 + kGatherWarps) {
         // ===== gather warps (alternate stages): X rows of every (position, channel chunk) stage into the raw ring, cp.async 16 B per lane =====
         // One warp instruction copies one 512 B row segment; the 16 rows of a stage complete on the stage's mbarrier
         // (cp.async.mbarrier.arrive.noinc from every lane).  Up to n_raw stages (8 KB each) are in flight towards this SM,
@@ -283,19 +288,22 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int bytes = col_ok ? 16 : 0;                      // src-size 0 => 16 bytes of zeros
         const int mine = warp - kGatherWarp0;
         int i = -1, cc = 0, o = -1;                              // stage counter and its (chunk, position of the issue order)
+        int slot = -1, turn = kGatherWarps - 1; uint32_t rph = 1u;   // the stage's ring slot / the parity its raw_empty is waited with / whose turn it is
         while (true) {
-            // next in-image stage, chunk-major; after the last chunk the bias stage
+            // next in-image stage, chunk-major; after the last chunk the bias stage (ring position kept incrementally: a runtime
+            // division per stage is ~150 cycles of a gather warp's ~460)
             int p;
             ++i;
+            if (++slot == geo.n_raw) { slot = 0; rph ^= 1u; }
+            if (++turn == kGatherWarps) turn = 0;
             if (i == n_stages - 1) p = kBiasPos;
             else if (i >= n_stages) break;
             else {
                 do { if (++o == U_pos) { o = 0; ++cc; } } while (!((vmask >> o) & 1u));
                 p = geo.pos_order[o];
             }
-            if ((i & 1) != mine) continue;
-            const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
-            { PROF_T0(30); mbar_wait(&raw_empty[slot], (uint32_t)((wr & 1) ^ 1)); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
+            if (turn != mine) continue;
+            { PROF_T0(30); mbar_wait(&raw_empty[slot], rph); if (tid == kGatherWarp0 * 32) PROF_ADD(30); }
             PROF_T0(31);
             float *dst = s_raw + (size_t)slot * (KS * BM) + lane * 4;
             // the 16 row indices first (4 x LDS.128), then 16 back-to-back copies: an index load in front of every copy
@@ -335,10 +343,11 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             for (int j = 0; j < 16; j++) z[j] = 0u;
             for (int c0 = 0; c0 < T * Gp; c0 += 16) tmem_store<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, z);
         }
+        int slot = sel - 2, sa = sel - 2; uint32_t rph = 0, aph = 1u;       // ring positions of this group's stages, kept incrementally (n_raw >= 3, n_a >= 2)
         for (int i = sel; i < n_stages; i += 2) {
-            const int wr = i / geo.n_raw, slot = i - wr * geo.n_raw;
-            const int wa = i / geo.n_a, sa = i - wa * geo.n_a;
-            { PROF_T0(20); mbar_wait(&raw_full[slot], (uint32_t)(wr & 1)); if (tid == 256) PROF_ADD(20); }
+            slot += 2; if (slot >= geo.n_raw) { slot -= geo.n_raw; rph ^= 1u; }
+            sa += 2; if (sa >= geo.n_a) { sa -= geo.n_a; aph ^= 1u; }
+            { PROF_T0(20); mbar_wait(&raw_full[slot], rph); if (tid == kProducerWarp0 * 32) PROF_ADD(20); }
             const float *src = src0 + (size_t)slot * (KS * BM);
             uint32_t hi[KS], lo[KS];
             { PROF_T0(21);
@@ -349,8 +358,8 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
             }
             mbar_arrive(&raw_empty[slot]);                      // the values are in registers: the slot can be refilled
-            if (tid == 256) PROF_ADD(21); }
-            { PROF_T0(23); mbar_wait(&emptyA[sa], (uint32_t)((wa & 1) ^ 1)); if (tid == 256) PROF_ADD(23); }
+            if (tid == kProducerWarp0 * 32) PROF_ADD(21); }
+            { PROF_T0(23); mbar_wait(&emptyA[sa], aph); if (tid == kProducerWarp0 * 32) PROF_ADD(23); }
             tc_fence_after();
             PROF_T0(24);
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + geo.a0 + (uint32_t)(sa * 32);
@@ -359,14 +368,14 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&fullA[sa]);
-            if (tid == 256) PROF_ADD(24);
+            if (tid == kProducerWarp0 * 32) PROF_ADD(24);
         }
-        if (tid == 256) PROF_SET(3);
+        if (tid == kProducerWarp0 * 32) PROF_SET(3);
 
         // ===== epilogue: TMEM -> registers -> ReLU -> Y rows of every pixel of the tile =====
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        if (tid == 256) PROF_SET(4);
+        if (tid == kProducerWarp0 * 32) PROF_SET(4);
         const int half = sel;                                    // two warps per lane quarter: even / odd 16-column chunks
         const int64_t ne = nbase + q * 32 + lane;
         if (!PEERS && geo.bulk_epi) {
@@ -428,7 +437,7 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (tid == 256) PROF_ADD(40); }
+                if (tid == kProducerWarp0 * 32) PROF_ADD(40); }
                 PROF_T0(41);
                 if (ne < n_vecs) {
                     if constexpr (!PEERS) {
@@ -461,12 +470,12 @@ pg_tile_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         }
                     }
                 }
-                if (tid == 256) PROF_ADD(41);
+                if (tid == kProducerWarp0 * 32) PROF_ADD(41);
             }
         }
     }
 
-    if (tid == 256) PROF_SET(5);
+    if (tid == kProducerWarp0 * 32) PROF_SET(5);
     tc_fence_before();
     __syncthreads();
     if (tid == 0) PROF_SET(6);
