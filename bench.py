@@ -24,6 +24,7 @@ cores on a bounded sample; `check` = parity of the very buffers that were timed 
 after the timed region.
 """
 import argparse
+import glob
 import hashlib
 import json
 import os
@@ -142,24 +143,30 @@ def tensor_peak():
 
 
 def lib_sha16():
-    from keynet_b200 import _native
+    """Identity of the kernel code the library is built from: sha256 over keynet_b200/csrc/* and include/*.h, in name order.
+    (Not the hash of the .so: a rebuild on another box embeds other source paths in its line tables and would read as stale.)"""
+    h = hashlib.sha256()
     try:
-        with open(_native.LIB_PATH, 'rb') as f:
-            return hashlib.sha256(f.read()).hexdigest()[:16]
+        files = sorted(glob.glob(os.path.join(ROOT, 'keynet_b200', 'csrc', '*')) + glob.glob(os.path.join(ROOT, 'include', '*.h')))
+        for f in files:
+            h.update(os.path.basename(f).encode())
+            with open(f, 'rb') as fh:
+                h.update(fh.read())
+        return h.hexdigest()[:16] if files else None
     except Exception:
         return None
 
 
 def profiled_traffic(net, batch, layer):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/traffic.json).  An entry is only valid for the library build it was captured from: entries carry the
-    sha256 of libkeynet_b200.so and are dropped (None) when the kernel code has changed since."""
+    capture (profiles/traffic.json).  An entry is only valid for the kernel code it was captured from: entries carry the
+    sha256 of the library's sources (lib_sha16) and are dropped (None) when the kernel code has changed since."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             t = json.load(f)
         e = t.get('%s:%d:%s' % (net, batch, layer))
         if isinstance(e, dict):
-            return (e.get('bytes'), None) if e.get('lib_sha16') == lib_sha16() else (None, 'capture %s is from another build of the library (stale)' % e.get('capture'))
+            return (e.get('bytes'), None) if e.get('lib_sha16') == lib_sha16() else (None, 'capture %s is from other kernel sources (stale)' % e.get('capture'))
         return (None, None if e is None else 'capture without a build hash (stale)')
     except Exception:
         return (None, None)
