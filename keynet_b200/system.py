@@ -31,79 +31,93 @@ def _tolist(x):
 
 
 # =============================================================================================
+def _unlink(table, kind):
+    """Take the layers whose name contains `kind` (dropout: the identity in eval()) out of the prev / next links of a netshape
+    table.  Their entries stay, so they still draw a key and numpy's RNG stream stays aligned with the reference's
+    (keynet/system.py:33-46) -- except names that are substrings of `kind` itself, which the reference's `k not in prefix`
+    drops from the table (kept for stream parity).  Chains of such layers are followed to their end."""
+    for v in table.values():
+        for link in ('nextlayer', 'prevlayer'):
+            while v[link] is not None and kind in v[link]:
+                v[link] = table[v[link]][link]
+    return OrderedDict((k, v) for (k, v) in table.items() if k not in kind)
+
+
+class _Keying(object):
+    """One keyed layer to build: where it goes in the keyed stack, the plain module it is compiled from, its shapes and keys."""
+    __slots__ = ('name', 'module', 'inshape', 'outshape', 'A', 'Ainv', 'relu_name', 'relu_module')
+
+    def __init__(self, name, module, inshape, outshape, A, Ainv, relu_name=None, relu_module=None):
+        (self.name, self.module, self.inshape, self.outshape, self.A, self.Ainv, self.relu_name, self.relu_module) = (name, module, inshape, outshape, A, Ainv, relu_name, relu_module)
+
+
 class KeyedModel(object):
     def __init__(self, net, inshape, inkey, f_layername_to_keypair, f_module_to_keyedmodule=None, do_output_encryption=False):
-        """Walk net.named_children(), give every layer an output key, chain them (Ainv of a layer is the
-        inverse output key of its predecessor), merge conv->relu and conv->bn, drop dropout, and compile each
-        keyed layer on the GPU (keynet/system.py:27-119)."""
+        """Key a plain network (keynet/system.py:27-119): every layer draws an output key pair, the input key of a layer is the
+        inverse output key of its predecessor, conv -> batchnorm and layer -> ReLU pairs are merged into one keyed layer,
+        dropout disappears, and every keyed layer is compiled on the GPU.
+
+        Three passes: draw the keys in the reference's order (the RNG stream is part of the contract), plan the merges
+        (_plan), build the planned layers."""
         net.eval()
-        netshape = _ktorch.netshape(net, inshape)
-
-        # dropout is the identity in eval(): unlink it.  As in the reference the entries stay in the table, so
-        # they still draw a key below and the RNG stream stays aligned (system.py:33-46).
-        for prefix in ['dropout']:
-            netshape = OrderedDict((k, v) for (k, v) in netshape.items() if k not in prefix)
-            for (k, v) in netshape.items():
-                if v['nextlayer'] is not None and prefix in v['nextlayer']:
-                    v['nextlayer'] = netshape[v['nextlayer']]['nextlayer']
-                elif v['prevlayer'] is not None and prefix in v['prevlayer']:
-                    v['prevlayer'] = netshape[v['prevlayer']]['prevlayer']
-
-        o = netshape['output']['prevlayer']
-        outkeys = OrderedDict((k, f_layername_to_keypair(k, v['outshape'])) for (k, v) in netshape.items() if k not in ('input', 'output'))
-        layerkey = {k: {'A': outkeys[k][0] if (k != o or do_output_encryption) else None,
-                        'Ainv': inkey if netshape[k]['prevlayer'] == 'input' else outkeys[netshape[k]['prevlayer']][1]}
-                    for k in outkeys}
-        layerkey['input'] = inkey
-        layerkey['output'] = outkeys[o][1] if do_output_encryption else None
+        shapes = _unlink(_ktorch.netshape(net, inshape), 'dropout')
+        last = shapes['output']['prevlayer']
+        pairs = OrderedDict((k, f_layername_to_keypair(k, v['outshape'])) for (k, v) in shapes.items() if k not in ('input', 'output'))
+        out_key = {k: (A if (k != last or do_output_encryption) else None) for (k, (A, _)) in pairs.items()}
+        in_key = {k: (inkey if shapes[k]['prevlayer'] == 'input' else pairs[shapes[k]['prevlayer']][1]) for k in pairs}
 
         keyed = OrderedDict()
-        for (k, m) in net.named_children():
+        for job in self._plan(net, shapes, out_key, in_key):
             if verbose():
-                print('[keynet_b200.KeyedModel]: Keying "%s"' % k)
-            assert k in layerkey, 'Key not found for layer "%s"' % k
-            assert k in netshape, 'Layer name not found in net shape for layer "%s"' % k
-            shp = netshape[k]
-
-            if isinstance(m, nn.BatchNorm2d):
-                assert '_bn' in k, "Batchnorm layers must be named 'mylayername_bn' for corresponding linear layer mylayername.  (e.g. 'conv3_bn')"
-                k_prev = k.split('_')[0]
-                assert shp['prevlayer'] == k_prev, "Batchnorm layer named 'mylayer_bn' must come right after 'mylayer' (e.g. 'conv3_bn' must come right after 'conv3')"
-                m_prev = copy.deepcopy(getattr(net, k_prev))
-                (w, b) = _ktorch.fuse_conv2d_and_bn(m_prev.weight, m_prev.bias, m.running_mean, m.running_var, 1E-5, m.weight, m.bias)
-                (m_prev.weight, m_prev.bias) = (torch.nn.Parameter(w), torch.nn.Parameter(b))
-                B = layerkey[k]['A'].dot(layerkey[k]['Ainv'])   # batchnorm out-key times inverse conv out-key
-                keyed[k_prev] = f_module_to_keyedmodule(m_prev, netshape[k_prev]['inshape'], shp['outshape'], B.dot(layerkey[k_prev]['A']), layerkey[k_prev]['Ainv'])
-
-            elif isinstance(m, nn.ReLU):
-                k_prev = shp['prevlayer']
-                if '_bn' not in k_prev:
-                    # key the skipped predecessor with the ReLU's out-key.  The effective key is evaluated as
-                    # (A_relu . A_prev^-1) . A_prev in fp32, exactly like the reference (system.py:90-91): with
-                    # gain keys its diagonal is fl32(fl32(a.(1/d)).d), not a -- simplifying it changes last bits.
-                    B = layerkey[k]['A'].dot(layerkey[k]['Ainv'])
-                    L = f_module_to_keyedmodule(getattr(net, k_prev), netshape[k_prev]['inshape'], netshape[k_prev]['outshape'], B.dot(layerkey[k_prev]['A']), layerkey[k_prev]['Ainv'])
-                    keyed[k_prev] = L.fuse_relu(True) if hasattr(L, 'fuse_relu') else L
-                    keyed[k] = _layer.FusedReLU() if hasattr(L, 'fuse_relu') else copy.deepcopy(m)
-                else:
-                    warnings.warn('Keying ReLU since previous layer "%s" is already keyed - Avoid sequential batchnorm and ReLU layers for efficient keying' % k_prev)
-                    keyed[k] = f_module_to_keyedmodule(m, shp['inshape'], shp['outshape'], layerkey[k]['A'], layerkey[k]['Ainv'])
-
-            elif isinstance(m, nn.Dropout):
-                pass
-            elif shp['nextlayer'] is not None and (('%s_bn' % k) == shp['nextlayer'] or 'relu' in shp['nextlayer']):
-                pass    # merged into the batchnorm / ReLU that follows
+                print('[keynet_b200.KeyedModel]: Keying "%s"' % job.name)
+            L = f_module_to_keyedmodule(job.module, job.inshape, job.outshape, job.A, job.Ainv)
+            if job.relu_name is not None:
+                # a keyed layer that can apply the ReLU itself keeps an identity placeholder under the ReLU's name
+                fused = hasattr(L, 'fuse_relu')
+                keyed[job.name] = L.fuse_relu(True) if fused else L
+                keyed[job.relu_name] = _layer.FusedReLU() if fused else copy.deepcopy(job.relu_module)
             else:
-                keyed[k] = f_module_to_keyedmodule(m, shp['inshape'], shp['outshape'], layerkey[k]['A'], layerkey[k]['Ainv'])
-            if verbose() and k in keyed:
-                print('[keynet_b200.KeyedModel]:     %s' % str(keyed[k]))
+                keyed[job.name] = L
+            if verbose():
+                print('[keynet_b200.KeyedModel]:     %s' % str(keyed[job.name]))
 
         self._keynet = nn.Sequential(keyed)
-        self._embeddingkey = layerkey['output']
-        self._imagekey = layerkey['input']
+        self._embeddingkey = pairs[last][1] if do_output_encryption else None
+        self._imagekey = inkey
         self._layernames = set(k for (k, m) in net.named_children())
-        self._outshape = netshape['output']['outshape']
-        self._netshape = netshape
+        self._outshape = shapes['output']['outshape']
+        self._netshape = shapes
+
+    @staticmethod
+    def _plan(net, shapes, out_key, in_key):
+        """The keyed layers to build, in stack order.  A layer followed by its batchnorm or by a ReLU is not keyed by itself:
+        the follower keys it with the follower's output key, evaluated as (A_f . A_f_in) . A_layer in fp32 -- the
+        reference's association (keynet/system.py:79-80,90-91); with gain keys the diagonal is fl32(fl32(a.(1/d)).d), not a."""
+        for (k, m) in net.named_children():
+            assert k in shapes and (k in out_key), 'layer "%s" of the network is missing from its shape table' % k
+            v = shapes[k]
+            if isinstance(m, nn.Dropout):
+                continue
+            if isinstance(m, nn.BatchNorm2d):
+                conv = k.split('_')[0]
+                assert '_bn' in k and v['prevlayer'] == conv, \
+                    'a batchnorm layer must be named "<layer>_bn" and follow "<layer>" directly (e.g. conv3, conv3_bn); got "%s" after "%s"' % (k, v['prevlayer'])
+                folded = copy.deepcopy(getattr(net, conv))
+                (w, b) = _ktorch.fuse_conv2d_and_bn(folded.weight, folded.bias, m.running_mean, m.running_var, 1E-5, m.weight, m.bias)
+                (folded.weight, folded.bias) = (torch.nn.Parameter(w), torch.nn.Parameter(b))
+                yield _Keying(conv, folded, shapes[conv]['inshape'], v['outshape'], out_key[k].dot(in_key[k]).dot(out_key[conv]), in_key[conv])
+            elif isinstance(m, nn.ReLU):
+                prev = v['prevlayer']
+                if '_bn' in prev:
+                    warnings.warn('ReLU "%s" follows the batchnorm-merged layer "%s" and is keyed as a layer of its own; avoid batchnorm + ReLU sequences for efficient keying' % (k, prev))
+                    yield _Keying(k, m, v['inshape'], v['outshape'], out_key[k], in_key[k])
+                else:
+                    yield _Keying(prev, getattr(net, prev), shapes[prev]['inshape'], shapes[prev]['outshape'],
+                                  out_key[k].dot(in_key[k]).dot(out_key[prev]), in_key[prev], relu_name=k, relu_module=m)
+            elif v['nextlayer'] is not None and (v['nextlayer'] == '%s_bn' % k or 'relu' in v['nextlayer']):
+                continue                                         # keyed by the batchnorm / ReLU that follows
+            else:
+                yield _Keying(k, m, v['inshape'], v['outshape'], out_key[k], in_key[k])
 
     def __repr__(self):
         return self._keynet.__repr__()
