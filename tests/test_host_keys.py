@@ -139,6 +139,82 @@ def test_monomial_key_algebra():
     assert np.array_equal(ref.indices, got.indices) and np.array_equal(ref.data.view(np.uint32), got.data.view(np.uint32))
 
 
+def test_lazy_identity_and_unscaled_keys_equal_explicit_ones():
+    """MonomialKey.identity(n) and keys without a value array (all ones) never build their 3.2 M-element arrays on the VGG16
+    keying path; every product / transpose / augmentation must still be bit-identical to the explicit form."""
+    rs = np.random.RandomState(4)
+    n = 40
+    I = sparse.MonomialKey.identity(n)
+    Ie = sparse.MonomialKey(np.arange(n), np.ones(n, dtype=np.float32))
+    P = sparse.MonomialKey(rs.permutation(n))                                            # unscaled: no value array
+    Pe = sparse.MonomialKey(P.perm.copy(), np.ones(n, dtype=np.float32))
+    D = sparse.MonomialKey(np.arange(n), (rs.rand(n) + 0.5).astype(np.float32))          # diagonal gain
+    G = sparse.MonomialKey(rs.permutation(n), (rs.rand(n) + 0.5).astype(np.float32))
+    assert I._perm is None and I._scale is None and I.is_identity() and I.nnz == n and P._scale is None
+    assert P.is_unscaled() and not P.is_unpermuted() and D.is_unpermuted() and not D.is_unscaled()
+
+    def same(X, Y):
+        return np.array_equal(X.perm, Y.perm) and np.array_equal(X.scale.view(np.uint32), Y.scale.view(np.uint32)) and X.shape == Y.shape
+
+    for (X, Xe) in ((I, Ie), (P, Pe)):
+        for K in (P, D, G, I):
+            assert same(X.dot(K), Xe.dot(K)) and same(K.dot(X), K.dot(Xe))
+        assert same(X.transpose(), Xe.transpose())
+        assert same(sparse.sparse_affine_to_linear(X), sparse.sparse_affine_to_linear(Xe))
+    assert I.dot(G) is G and G.dot(I) is G and D.transpose() is D                        # no copies for the trivial cases
+    assert sparse.sparse_affine_to_linear(I).is_identity() and sparse.sparse_affine_to_linear(I)._perm is None
+    assert same(P.dot(P.transpose()), Ie) and P.dot(P.transpose()).is_identity()
+    assert np.array_equal(I.todense(), np.eye(n, dtype=np.float32))
+    # a homogeneous gain key keeps its trailing one
+    H = sparse.sparse_affine_to_linear(D)
+    assert H.perm[-1] == n and H.scale[-1] == 1.0 and np.array_equal(H.scale[:n], D.scale)
+
+
+def test_keyed_model_plan_merges_and_dropout_links():
+    """KeyedModel's three passes on the host: dropout leaves the links but keeps its table entry (it still draws a key), a layer
+    followed by ReLU / its batchnorm is keyed by the follower with (A_f . A_f_in) . A_layer."""
+    import torch
+    from collections import OrderedDict
+    from torch import nn
+    table = OrderedDict([('input', {'prevlayer': None, 'nextlayer': 'fc1'}), ('fc1', {'prevlayer': 'input', 'nextlayer': 'dropout1'}),
+                         ('dropout1', {'prevlayer': 'fc1', 'nextlayer': 'dropout2'}), ('dropout2', {'prevlayer': 'dropout1', 'nextlayer': 'fc2'}),
+                         ('fc2', {'prevlayer': 'dropout2', 'nextlayer': 'output'}), ('output', {'prevlayer': 'fc2', 'nextlayer': None})])
+    t = system._unlink(table, 'dropout')
+    assert list(t) == list(table) and t['fc1']['nextlayer'] == 'fc2' and t['fc2']['prevlayer'] == 'fc1'
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(1, 2, 3, padding=1); self.conv1_bn = nn.BatchNorm2d(2); self.conv2 = nn.Conv2d(2, 2, 3, padding=1)
+            self.relu2 = nn.ReLU(); self.dropout2 = nn.Dropout(); self.fc = nn.Linear(2 * 4 * 4, 3)
+
+        def forward(self, x):
+            return self.fc(self.dropout2(self.relu2(self.conv2(self.conv1_bn(self.conv1(x))))).flatten(1))
+    net = Net().eval()
+    from keynet_b200 import torch as ktorch
+    shapes = system._unlink(ktorch.netshape(net, (1, 4, 4)), 'dropout')
+    rs = np.random.RandomState(0)
+    keys = {}
+    for (k, v) in shapes.items():
+        if k in ('input', 'output'):
+            continue
+        n = int(np.prod(v['outshape'])) + 1
+        A = sparse.MonomialKey(np.concatenate([rs.permutation(n - 1), [n - 1]]), np.concatenate([rs.rand(n - 1) + 0.5, [1.0]]).astype(np.float32))
+        keys[k] = (A, sparse.MonomialKey(A.transpose().perm, (1.0 / A.transpose().scale).astype(np.float32)))
+    inkey = sparse.MonomialKey.identity(17)
+    out_key = {k: A for (k, (A, _)) in keys.items()}
+    in_key = {k: (inkey if shapes[k]['prevlayer'] == 'input' else keys[shapes[k]['prevlayer']][1]) for k in keys}
+    jobs = list(system.KeyedModel._plan(net, shapes, out_key, in_key))
+    assert [(j.name, j.relu_name) for j in jobs] == [('conv1', None), ('conv2', 'relu2'), ('fc', None)]
+    (c1, c2, fc) = jobs
+    assert c1.module is not net.conv1 and not torch.equal(c1.module.weight, net.conv1.weight)      # batchnorm folded into a copy
+    expect = out_key['conv1_bn'].dot(in_key['conv1_bn']).dot(out_key['conv1'])
+    assert np.array_equal(c1.A.perm, expect.perm) and np.array_equal(c1.A.scale, expect.scale) and c1.Ainv is inkey
+    expect = out_key['relu2'].dot(in_key['relu2']).dot(out_key['conv2'])
+    assert np.array_equal(c2.A.perm, expect.perm) and np.array_equal(c2.A.scale, expect.scale) and c2.Ainv is keys['conv1_bn'][1]
+    assert fc.Ainv is keys['relu2'][1] and fc.A is out_key['fc']          # the dropout between relu2 and fc is gone from the links
+
+
 def test_permutation_consumes_same_rng_stream_as_reference_form():
     np.random.seed(5)
     a = np.random.permutation(list(range(0, 37)))      # reference form (sparse.py:283)
