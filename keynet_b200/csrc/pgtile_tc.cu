@@ -11,19 +11,20 @@
 //   * under permutation-only keys every pixel multiplies the SAME weight matrix, so the P*Q tap slabs of a channel chunk
 //     are loaded ONCE per chunk by TMA into a slab ring and reused by every pixel of the tile at its own position
 //     (tap of pixel t at union position p = p - t*stride); taps that fall outside the image are simply not issued;
-//   * every pixel has its own fp32 accumulator in TMEM.  A thread issues one tcgen05.mma per ~85-117 cycles whatever its
-//     shape and a 128 x 64 x 8 tf32 MMA occupies the pipe for ~36, so one instruction per (pixel, tap) leaves the kernel bound
-//     by the issuers' instruction rate (measured: ~850 cycles per pixel-stage for 216 cycles of tensor pipe).  With stride 1
-//     the pixels of one tile ROW that use a gathered position read CONSECUTIVE taps of one tap row (pixel tx at union column
-//     px uses tap dx = px - tx), so with the accumulators of a row laid out in descending tx and the hi (lo) planes of the
-//     tap slabs contiguous in shared memory, ONE tcgen05.mma of N = (pixels in the run) x Gp multiplies the stage by all of
-//     them.  A thread issues one tcgen05.mma per ~143 cycles whatever N and whichever accumulator it targets
-//     (scratch/umma_rate.cu: only N = 256 from one thread, or N = 128 from two, ... reach the pipe rate of 0.56 N cycles), so
-//     what counts is instructions PER ISSUER THREAD: every tile row has two issuers, one per 8-k half of the 16-k stage, both
-//     accumulating into the row's accumulators (zeroed up front: no issuer owns the first write).  2x2 tile, 3x3 taps:
-//     36 instructions per issuer and chunk (54 with one issuer per pixel) against 7.8 k cycles of tensor pipe.  A slab is
-//     waited for once and released once per chunk and issuer (first / last use), not per use.  Other strides: one issuer and
-//     one instruction per (pixel, tap) as before;
+//   * every pixel has its own fp32 accumulator in TMEM.  With stride 1 the pixels of one tile ROW that use a gathered position
+//     read CONSECUTIVE taps of one tap row (pixel tx at union column px uses tap dx = px - tx), so with the accumulators of a
+//     row laid out in descending tx and the hi (lo) planes of the tap slabs contiguous in shared memory, ONE tcgen05.mma of
+//     N = (pixels in the run) x Gp multiplies the stage by all of them (N = 128 .. 256 instead of 64 .. 128);
+//   * issuers are elected threads (kn_tc::elect_one -- under `if (lane == 0)` every tcgen05.mma cost 127-143 cycles of an
+//     ELECT / R2UR loop, under elect.sync one thread issues at the pipe rate), and an issuer is ONE thread running ~4-6 cycles
+//     per dependent scalar instruction, so what counts is instructions per issuer and stage: every tile row has two issuers,
+//     one per 8-k half of the 16-k stage, both accumulating into the row's accumulators (zeroed up front: no issuer owns the
+//     first write); what an issuer does at a position is a host-built record (kernel parameter), and for the 3x3 / stride-1
+//     geometries the whole schedule is folded at compile time (issuer_fast).  A slab is waited for once and released once
+//     per chunk and issuer (first / last use), not per use.  Other strides: one issuer and one instruction per (pixel, tap);
+//   * gathers: seven warps, cp.async 16 B per lane into a raw shared-memory ring that completes on mbarriers (16 stages =
+//     128 KB in flight towards the SM for G = 64); two splitter groups (hi / lo split -> tcgen05.st) on alternate stages;
+//   * output rows are transposed through the (by then idle) gather ring and leave as 512-byte cp.async.bulk rows;
 //   * A operand (gathered activations, hi/lo split in registers) in a TMEM ring exactly as in pgroup_tc.cu; 3xTF32
 //     (hi.hi + lo.hi + hi.lo), bias as one extra stage reading the homogeneous row.
 // L2 -> SM bytes per (pixel, 16-channel chunk): G = 64: 108 KB -> 50 KB, G = 96: 126 -> 59, G = 128: 216 -> 120.
